@@ -1,0 +1,253 @@
+/* krep_b200.h — C ABI of the B200-native scan engine that drops in behind krep's
+ * search_func_t boundary.
+ *
+ * Every entry point below names the reference interface it replaces as
+ * (file:line) into davidesantangelo/krep v2.2.0.  The data types are restated
+ * byte-for-byte from krep.h:49-101 so that a krep host can pass its own
+ * search_params_t / match_result_t straight through; if krep.h was included
+ * first (KREP_H defined) the restatement is skipped and krep's own types are used.
+ *
+ * Nothing in this header mentions torch, CUDA runtime types or C++: plain
+ * pointers and sizes only.  Device pointers are passed as const void* and
+ * streams as void* (a cudaStream_t).
+ */
+#ifndef KREP_B200_H
+#define KREP_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* Types restated from krep.h (layout-identical; checked by static asserts   */
+/* in csrc/abi_check.cpp and tests/test_abi.py)                              */
+/* ------------------------------------------------------------------------- */
+#ifndef KREP_H
+
+/* krep.h:49-53 */
+typedef struct
+{
+   size_t start_offset; /* first byte of the match, relative to text_start   */
+   size_t end_offset;   /* one past the last byte                             */
+} match_position_t;
+
+/* krep.h:55-60 — positions must be malloc-family memory (krep.c:244-251)     */
+typedef struct match_result_t
+{
+   match_position_t *positions;
+   uint64_t count;
+   uint64_t capacity;
+} match_result_t;
+
+struct ac_trie;
+typedef struct ac_trie ac_trie_t; /* krep.h:22-23, opaque */
+
+/* krep.h:65-94 */
+typedef struct search_params
+{
+   const char *pattern; /* single-literal kernels read these two (krep.c:1271) */
+   size_t pattern_len;
+
+   const char **patterns; /* multi-literal kernel reads these three            */
+   size_t *pattern_lens;
+   size_t num_patterns;
+
+   bool case_sensitive;
+   bool use_regex;
+   bool count_lines_mode;   /* -c   */
+   bool count_matches_mode; /* -co  */
+   bool track_positions;    /* !(-c && !-o) */
+   bool whole_word;         /* -w   */
+
+   const void *compiled_regex; /* const regex_t* in krep.h; unused on this path */
+   ac_trie_t *ac_trie;
+   size_t max_count; /* SIZE_MAX = unlimited */
+} search_params_t;
+
+/* krep.h:98-101 */
+typedef uint64_t (*search_func_t)(const search_params_t *params,
+                                  const char *text_start,
+                                  size_t text_len,
+                                  match_result_t *result);
+#endif /* KREP_H */
+
+/* ------------------------------------------------------------------------- */
+/* Lifetime                                                                  */
+/* ------------------------------------------------------------------------- */
+
+/* Bind the calling process to one CUDA device and create the engine context
+ * (streams, pinned staging ring, device scratch).  Optional: every entry point
+ * initialises lazily on the current device.  Returns 0, or a negative value
+ * after printing "krep: ..." to stderr (the reference's error convention,
+ * krep.c:1933).  There is no CPU fallback: without a usable sm_100 device every
+ * search entry point prints an error and aborts the call with count 0 and
+ * krep_b200_last_error() != 0. */
+int krep_b200_init(int device);
+void krep_b200_shutdown(void);
+int krep_b200_last_error(void);           /* 0 = last call succeeded          */
+const char *krep_b200_last_error_string(void);
+const char *krep_b200_version(void);
+
+/* ------------------------------------------------------------------------- */
+/* The file-static globals of krep.c that the kernels read (krep.c:117-120). */
+/* A host that links this library mirrors its own flags into these.          */
+/* ------------------------------------------------------------------------- */
+void krep_b200_set_only_matching(bool on); /* -o            krep.c:117 */
+bool krep_b200_get_only_matching(void);
+void krep_b200_set_force_no_simd(bool on); /* --no-simd     krep.c:118 */
+void krep_b200_set_algo_override(const char *name); /* --algo=auto|bm|kmp krep.c:120; NULL = auto */
+
+/* ------------------------------------------------------------------------- */
+/* search_func_t replacements (host text in, match_result_t out).            */
+/* Each reproduces the count, the offsets and their order of the named       */
+/* reference function called once on the whole buffer (krep -t 1 semantics,  */
+/* SURVEY §8 a12), including its overlap policy, -w/-c/-m behaviour.          */
+/* ------------------------------------------------------------------------- */
+uint64_t krep_b200_boyer_moore_search(const search_params_t *, const char *, size_t, match_result_t *);  /* krep.c:1260 */
+uint64_t krep_b200_kmp_search(const search_params_t *, const char *, size_t, match_result_t *);          /* krep.c:1628 */
+uint64_t krep_b200_memchr_search(const search_params_t *, const char *, size_t, match_result_t *);       /* krep.c:3891 */
+uint64_t krep_b200_memchr_short_search(const search_params_t *, const char *, size_t, match_result_t *); /* krep.c:4371 */
+uint64_t krep_b200_simd_sse42_search(const search_params_t *, const char *, size_t, match_result_t *);   /* krep.c:4702 */
+uint64_t krep_b200_simd_avx2_search(const search_params_t *, const char *, size_t, match_result_t *);    /* krep.c:4877 */
+uint64_t krep_b200_simd_avx512_search(const search_params_t *, const char *, size_t, match_result_t *);  /* krep.c:5108 */
+uint64_t krep_b200_aho_corasick_search(const search_params_t *, const char *, size_t, match_result_t *); /* aho_corasick.c:299 */
+
+/* krep.c:1771 — same decision order (regex excluded: returns NULL for
+ * use_regex, the caller keeps its own regex_search), same globals. The
+ * returned pointer is one of the eight functions above. */
+search_func_t krep_b200_select_search_algorithm(const search_params_t *params);
+/* krep.c:1964 */
+const char *krep_b200_get_algorithm_name(search_func_t func);
+
+/* aho_corasick.c:111 / 274 / 287.  The returned object is this library's own
+ * device automaton (patterns folded, filter tables and verify tables resident
+ * in HBM); krep_b200_aho_corasick_search also accepts a params->ac_trie that
+ * was built by the reference's ac_trie_build (it only tests it for NULL, as
+ * aho_corasick.c:306 does) and then compiles and caches its own automaton
+ * from params->patterns. */
+ac_trie_t *krep_b200_ac_trie_build(const search_params_t *params);
+void krep_b200_ac_trie_free(ac_trie_t *trie);
+bool krep_b200_ac_trie_root_has_outputs(const ac_trie_t *trie);
+
+/* krep.c:139 / 175 / 244 / 256 — for hosts that do not link krep.c. */
+match_result_t *krep_b200_match_result_init(uint64_t initial_capacity);
+bool krep_b200_match_result_add(match_result_t *result, size_t start_offset, size_t end_offset);
+void krep_b200_match_result_free(match_result_t *result);
+bool krep_b200_match_result_merge(match_result_t *dest, const match_result_t *src, size_t chunk_offset);
+
+/* ------------------------------------------------------------------------- */
+/* HBM-resident shard API — what search_chunk_thread (krep.c:1919) becomes   */
+/* when the chunk already lives on the GPU: one shard per device, owned      */
+/* range + halo, matches owned by start offset.                 */
+/* ------------------------------------------------------------------------- */
+
+/* Emulated reference kernel: selects the overlap / -w / -m policy applied to
+ * the raw occurrence list. */
+enum
+{
+   KREP_B200_ALGO_BMH = 0,          /* boyer_moore_search  krep.c:1260 */
+   KREP_B200_ALGO_KMP = 1,          /* kmp_search          krep.c:1628 */
+   KREP_B200_ALGO_MEMCHR = 2,       /* memchr_search       krep.c:3891 */
+   KREP_B200_ALGO_MEMCHR_SHORT = 3, /* memchr_short_search krep.c:4371 */
+   KREP_B200_ALGO_SSE42 = 4,        /* simd_sse42_search   krep.c:4702 */
+   KREP_B200_ALGO_AVX2 = 5,         /* simd_avx2_search    krep.c:4877 */
+   KREP_B200_ALGO_AVX512 = 6,       /* simd_avx512_search  krep.c:5108 */
+   KREP_B200_ALGO_AC = 7            /* aho_corasick_search aho_corasick.c:299 */
+};
+
+typedef struct krep_b200_plan krep_b200_plan_t; /* compiled pattern set, device-resident */
+
+/* Compile params->pattern (algo != AC) or params->patterns[] (algo == AC)
+ * into filter constants / tables on the current device. NULL on error. */
+krep_b200_plan_t *krep_b200_plan_create(const search_params_t *params, int algo);
+void krep_b200_plan_destroy(krep_b200_plan_t *plan);
+/* Which device filter the plan uses (for bench/config reporting). */
+const char *krep_b200_plan_filter_name(const krep_b200_plan_t *plan);
+
+/* One shard of a corpus that is resident in device memory. */
+typedef struct
+{
+   const void *d_text;     /* device pointer, 16-byte aligned                       */
+   uint64_t avail_len;     /* bytes readable at d_text: owned range + halo            */
+   uint64_t own_begin;     /* report matches whose start is in [own_begin, own_end)   */
+   uint64_t own_end;       /*   (offsets relative to d_text)                          */
+   uint64_t global_offset; /* added to every reported offset                          */
+   int32_t prev_byte;      /* byte preceding d_text[0] in the whole text, -1 = none   */
+   int32_t next_byte;      /* byte following d_text[avail_len-1], -1 = end of text    */
+} krep_b200_shard_t;
+
+/* Result of a device scan, left in device memory (sorted ascending). */
+typedef struct
+{
+   uint64_t count;          /* occurrences found (exact even if capacity was exceeded) */
+   uint64_t stored;         /* entries actually stored = min(count, capacity)           */
+   const uint64_t *d_keys;  /* device: literal: start offset (global); AC: packed key   */
+   int overflow;            /* 1 if count > capacity: call again with a larger capacity */
+} krep_b200_device_result_t;
+
+/* Scan one shard on `stream` (cudaStream_t, NULL = engine stream): launches the
+ * filter+verify kernel and sorts the occurrence list on the device. For a
+ * literal plan every key is the global start offset of one occurrence that
+ * passed the plan's -w filter.  For an AC plan every key packs
+ * (end_offset << 24 | (1023 - (len-1)) << 10 ... see krep_b200_ac_key_* below) so
+ * that ascending key order is aho_corasick_search's emission order.
+ * `want_positions` = 0 counts only (no list is written).
+ * Blocks until the count is known. Returns 0 or a negative error. */
+int krep_b200_scan_shard(const krep_b200_plan_t *plan, const krep_b200_shard_t *shard,
+                         int want_positions, void *stream, krep_b200_device_result_t *out);
+
+/* Timing hook for bench.py: device time in milliseconds of the scan kernel(s)
+ * of the most recent krep_b200_scan_shard / search call on this thread,
+ * measured with CUDA events on the launching stream (kernel only, no sort). */
+float krep_b200_last_kernel_ms(void);
+/* Number of kernel launches issued by this library since the last reset. */
+uint64_t krep_b200_launch_count(void);
+void krep_b200_reset_launch_count(void);
+
+/* Apply the emulated reference kernel's policy (overlap rule, -m cap) to a
+ * shard result and deliver it as krep's match_result_t (host, malloc memory).
+ * Count-lines mode needs host text and is only available through the
+ * search_func_t entry points. Returns the count the reference would return. */
+uint64_t krep_b200_collect(const krep_b200_plan_t *plan, const search_params_t *params,
+                           const krep_b200_device_result_t *dev, match_result_t *result);
+
+/* AC key layout helpers */
+uint64_t krep_b200_ac_key_end(uint64_t key);
+uint64_t krep_b200_ac_key_start(uint64_t key);
+uint32_t krep_b200_ac_key_pattern(uint64_t key);
+
+/* ------------------------------------------------------------------------- */
+/* Synthetic corpus: byte[i] is a pure function of (seed, i), so */
+/* any shard can be materialised in place on any GPU without transfers.      */
+/* ------------------------------------------------------------------------- */
+typedef struct
+{
+   uint64_t seed;            /* text seed                                          */
+   uint64_t plant_seed;      /* needle placement seed                              */
+   uint64_t plant_period;    /* one planted needle per this many bytes (0 = none)  */
+   const char *needle;       /* host pointer, needle_len bytes (copied)            */
+   uint32_t needle_len;      /* <= 64                                              */
+   uint32_t flags;           /* KREP_B200_CORPUS_*                                 */
+} krep_b200_corpus_spec_t;
+
+enum
+{
+   KREP_B200_CORPUS_RANDOM_CASE = 1, /* planted needles get per-letter pseudo-random case   */
+   KREP_B200_CORPUS_EMBED_HALF = 2   /* odd-numbered plants are glued inside a longer word  */
+};
+
+/* Fill d_dst[0..len) with corpus bytes [global_offset, global_offset+len). */
+int krep_b200_corpus_generate(const krep_b200_corpus_spec_t *spec, void *d_dst,
+                              uint64_t global_offset, uint64_t len, void *stream);
+/* Host twin of the generator (same bytes), for tests and the CPU baseline. */
+int krep_b200_corpus_generate_host(const krep_b200_corpus_spec_t *spec, void *dst,
+                                   uint64_t global_offset, uint64_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KREP_B200_H */
