@@ -215,6 +215,16 @@ void krep_b200_reset_launch_count(void);
 uint64_t krep_b200_collect(const krep_b200_plan_t *plan, const search_params_t *params,
                            const krep_b200_device_result_t *dev, match_result_t *result);
 
+/* Policy replay over a caller-supplied, ascending occurrence-key list in HOST memory (what
+ * krep_b200_collect does after reading the device list back).  A multi-GPU host gathers the
+ * per-shard lists (already globally ordered across ranks), concatenates them and calls
+ * this once, which is the analogue of the reference's merge step (krep.c:2928-3004) without its
+ * chunk-edge artefacts.  `text`/`text_len` may be NULL/0 unless params->count_lines_mode is set.
+ * `algo` is a KREP_B200_ALGO_* value; `only_matching` is the -o global to emulate. */
+uint64_t krep_b200_replay(int algo, const search_params_t *params, bool only_matching,
+                          const uint64_t *keys, uint64_t nkeys,
+                          const char *text, size_t text_len, match_result_t *result);
+
 /* AC key layout helpers */
 uint64_t krep_b200_ac_key_end(uint64_t key);
 uint64_t krep_b200_ac_key_start(uint64_t key);

@@ -1,0 +1,139 @@
+// common.h — internal declarations shared by the engine's translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include "../../include/krep_b200.h"
+
+namespace kb {
+
+// ---------------------------------------------------------------------------------------------
+// Occurrence keys.  Every occurrence the device reports is one 64-bit key; ascending key order is
+// the order the emulated reference kernel would have produced.
+//   literal plans : key = (global_start << 2) | (full << 1) | ww_ok
+//                   full  = all pattern_len bytes match (always 1 unless the plan emits prefix hits,
+//                           which only memchr_short_search's -o walk needs, krep.c:4495)
+//                   ww_ok = is_whole_word_match(start, start+len)  (krep.h:312) — 1 when -w is off
+//   AC plans      : key = (global_end << 24) | ((1023 - (len-1)) << 14) | pattern_index
+//                   (end ascending, then longest first, then pattern-list order: aho_corasick.c:353-431)
+// ---------------------------------------------------------------------------------------------
+static constexpr int LIT_TAG_BITS = 2;
+static constexpr int AC_END_SHIFT = 24;
+static constexpr int AC_LEN_SHIFT = 14;
+static constexpr uint32_t AC_MAX_PATTERNS = 1u << 14;
+
+enum FilterKind : int
+{
+    FILTER_ALIGNED4 = 0, // pattern_len >= 7: every occurrence contains one aligned 32-bit word; test each
+                         // aligned text word against the 4 pattern words P[d..d+4), d = 0..3
+    FILTER_WINDOW4 = 1,  // pattern_len < 7 (or prefix plans): test the 4-byte window at every byte offset
+};
+
+struct LitDevParams
+{
+    const uint8_t *text; // 16-byte aligned
+    uint64_t avail_len;
+    uint64_t own_begin, own_end;
+    uint64_t global_offset;
+    int32_t prev_byte, next_byte;
+    uint64_t group_begin, group_end; // 16-byte groups [group_begin, group_end) are scanned by the vector loop
+    uint64_t tail_start;             // starts >= tail_start are checked byte-wise by the tail warp
+    uint32_t m;                      // full pattern length
+    uint32_t emit_len;               // bytes that must match for a key to be emitted (== m, or 1 for prefix plans)
+    uint32_t K[4];                   // filter constants (already folded)
+    uint32_t fold;                   // AND-mask applied to text words before comparing (0xFFFFFFFF or 0xDFDFDFDF)
+    uint32_t win_mask;               // WINDOW4: mask of the low min(4, emit_len) bytes
+    const uint8_t *pat_val;          // device: pattern[k] & pat_mask[k]
+    const uint8_t *pat_mask;         // device: 0xDF where case folds, else 0xFF
+    uint64_t *out;                   // device key buffer (may be null when !want_positions)
+    uint64_t cap;
+    unsigned long long *counter;     // [0] = occurrences emitted (exact, also past cap)
+    uint32_t whole_word;             // 0 none, 1 drop failures on device, 2 tag only
+    uint32_t want_positions;
+};
+
+struct AcDevTables; // scan_multi.cu
+
+struct Plan
+{
+    int algo = 0;
+    bool is_ac = false;
+    // literal
+    std::string pattern;
+    bool case_sensitive = true;
+    uint32_t m = 0, emit_len = 0;
+    FilterKind filter = FILTER_ALIGNED4;
+    uint32_t K[4] = {0, 0, 0, 0};
+    uint32_t fold = 0xFFFFFFFFu, win_mask = 0xFFFFFFFFu;
+    uint32_t whole_word = 0;
+    uint8_t *d_pat_val = nullptr, *d_pat_mask = nullptr;
+    bool border_free = true; // no proper prefix is also a suffix: occurrences cannot overlap
+    bool built_only_matching = false; // value of the -o global the plan was compiled for
+    // AC
+    std::vector<std::string> patterns;
+    std::vector<uint32_t> pat_lens;
+    uint32_t min_len = 0, max_len = 0;
+    AcDevTables *ac = nullptr;
+    std::string filter_name;
+    uint64_t magic = 0x6b7265705f623230ull; // "krep_b20"
+};
+
+// engine.cu
+struct Engine;
+Engine &engine();
+bool engine_ok();
+void set_error(int code, const char *fmt, ...);
+void clear_error();
+
+struct ScanOut
+{
+    uint64_t count = 0, stored = 0;
+    const uint64_t *d_keys = nullptr;
+    int overflow = 0;
+};
+
+// Launch one shard scan on `stream`; appends to the engine's key list (no reset) when append=true.
+int launch_scan(const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream);
+// literal kernels (scan_literal.cu)
+void launch_literal(const Plan *plan, const LitDevParams &p, cudaStream_t s);
+// multi kernels (scan_multi.cu)
+int ac_build_tables(Plan *plan);
+void ac_free_tables(Plan *plan);
+struct AcLaunch
+{
+    const uint8_t *text;
+    uint64_t avail_len, own_begin, own_end, global_offset;
+    int32_t prev_byte, next_byte;
+    uint64_t *out;
+    uint64_t cap;
+    unsigned long long *counter;
+    uint32_t whole_word, want_positions;
+};
+void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t s);
+void count_launch(int n = 1);
+
+// semantics.cpp — reference control flow replayed over the sorted occurrence list
+struct Replay
+{
+    const uint64_t *keys;
+    size_t n;
+    const char *text; // host text (needed for -c line logic); may be null otherwise
+    size_t text_len;
+    uint64_t base; // global offset subtracted from key offsets
+};
+uint64_t replay_literal(int algo, const search_params_t *P, bool only_matching, uint32_t m,
+                        const Replay &r, match_result_t *res);
+uint64_t replay_ac(const search_params_t *P, const Replay &r, match_result_t *res);
+bool result_push(match_result_t *r, size_t s, size_t e);
+
+// C-locale helpers shared by host code (krep.c:125-134, krep.h:298-301)
+static inline unsigned char lower_c(unsigned char c) { return (c >= 'A' && c <= 'Z') ? (unsigned char)(c + 32) : c; }
+static inline bool is_alpha_c(unsigned char c) { return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'); }
+static inline bool is_word_c(int c)
+{
+    return (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_';
+}
+
+} // namespace kb

@@ -1,0 +1,611 @@
+// host_api.cu — the search_func_t-typed entry points (host text in, match_result_t out) and the rest of
+// the host-facing C ABI: option globals, dispatch (select_search_algorithm), AC trie handles,
+// match_result helpers.
+//
+// Data path of one call (north_star): the caller's buffer (krep's mmap, krep.c:2680) is staged into
+// HBM in chunks — straight from the caller's memory when it is already page-locked, otherwise through
+// a ring of pinned staging buffers filled by host threads — with cudaMemcpyAsync on a copy stream,
+// while the scan stream runs the filter kernel on every chunk whose bytes have landed.  All chunk
+// kernels append to one device occurrence list, which is sorted on the device, read back, and replayed
+// under the emulated kernel's policy (semantics.cpp).  There is no CPU scan anywhere on this path.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <omp.h>
+#include "common.h"
+#include "engine.h"
+
+namespace kb {
+
+// ---- krep.c:117-120 mirrored option globals ---------------------------------------------------
+static bool g_only_matching = false;
+static bool g_force_no_simd = false;
+static std::string g_algo_override; // "", "auto", "bm", "kmp"
+
+// The reference binary this library stands in for is the AVX2 build (Makefile:31-35, krep.c:47-59):
+// KREP_USE_AVX2 = KREP_USE_SSE42 = 1, SIMD_MAX_PATTERN_LEN = 32 (krep.c:104-106).
+static constexpr size_t SIMD_MAX_PATTERN_LEN = 32;
+
+// Precondition fallbacks of the simd_* entry points (krep.c:4708-4712, 4883-4895, 5115-5126).
+int resolve_algo(const search_params_t *P, int algo)
+{
+    const size_t m = P->pattern_len;
+    if (algo == KREP_B200_ALGO_AVX512)
+    {
+        if (m == 0 || m > 64 || !P->case_sensitive) return KREP_B200_ALGO_BMH;
+        if (m <= 32) algo = KREP_B200_ALGO_AVX2;
+    }
+    if (algo == KREP_B200_ALGO_AVX2)
+    {
+        if (m == 0 || m > 32 || !P->case_sensitive) return KREP_B200_ALGO_BMH;
+        if (m <= 16) algo = KREP_B200_ALGO_SSE42;
+    }
+    if (algo == KREP_B200_ALGO_SSE42)
+    {
+        if (m == 0 || m > 16 || !P->case_sensitive) return KREP_B200_ALGO_BMH;
+    }
+    return algo;
+}
+
+// ---- plan cache ---------------------------------------------------------------------------------
+static bool plan_matches(const Plan *pl, const search_params_t *P, int algo, bool only_matching)
+{
+    if (pl->algo != algo || pl->case_sensitive != P->case_sensitive) return false;
+    if (pl->is_ac)
+    {
+        if ((pl->whole_word != 0) != P->whole_word) return false;
+        if (pl->patterns.size() != P->num_patterns) return false;
+        for (size_t k = 0; k < P->num_patterns; k++)
+        {
+            if (pl->pat_lens[k] != P->pattern_lens[k]) return false;
+            if (P->pattern_lens[k] && memcmp(pl->patterns[k].data(), P->patterns[k], P->pattern_lens[k]) != 0) return false;
+        }
+        return true;
+    }
+    size_t m = algo == KREP_B200_ALGO_MEMCHR ? (P->pattern_len ? 1 : 0) : P->pattern_len;
+    if (pl->m != m || memcmp(pl->pattern.data(), P->pattern, m) != 0) return false;
+    if ((pl->whole_word != 0) != P->whole_word) return false;
+    return pl->built_only_matching == only_matching;
+}
+
+static Plan *cached_plan(const search_params_t *P, int algo, bool only_matching)
+{
+    Engine &E = engine();
+    for (size_t i = 0; i < E.plan_cache.size(); i++)
+        if (plan_matches(E.plan_cache[i], P, algo, only_matching))
+        {
+            Plan *pl = E.plan_cache[i];
+            E.plan_cache.erase(E.plan_cache.begin() + i);
+            E.plan_cache.push_back(pl); // most recent last
+            return pl;
+        }
+    Plan *pl = plan_build(P, algo, only_matching);
+    if (!pl) return nullptr;
+    if (E.plan_cache.size() >= 16)
+    {
+        plan_free(E.plan_cache.front());
+        E.plan_cache.erase(E.plan_cache.begin());
+    }
+    E.plan_cache.push_back(pl);
+    return pl;
+}
+
+// ---- staging: host text -> HBM, overlapped with the scan ----------------------------------------
+#define CKH(call)                                                                                  \
+    do                                                                                             \
+    {                                                                                              \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+        {                                                                                          \
+            set_error(-2, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                      cudaGetErrorString(e_));                                                     \
+            return -2;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+static size_t env_mb(const char *name, size_t dflt_mb)
+{
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt_mb << 20;
+    long x = atol(v);
+    return x > 0 ? (size_t)x << 20 : dflt_mb << 20;
+}
+
+static int ensure_text(uint64_t n)
+{
+    Engine &E = engine();
+    const uint64_t need = ((n + 63) & ~63ull) + 64;
+    if (need <= E.text_cap) return 0;
+    CKH(cudaStreamSynchronize(E.scan_stream));
+    CKH(cudaStreamSynchronize(E.copy_stream));
+    cudaFree(E.d_text);
+    E.d_text = nullptr;
+    E.text_cap = 0;
+    uint64_t cap = need + need / 16; // a little slack so slightly larger files do not reallocate
+    cudaError_t e = cudaMalloc(&E.d_text, cap);
+    if (e != cudaSuccess)
+    {
+        cap = need;
+        e = cudaMalloc(&E.d_text, cap);
+    }
+    if (e != cudaSuccess)
+    {
+        set_error(-2, "cannot allocate %llu bytes of HBM for the text (%s)", (unsigned long long)cap, cudaGetErrorString(e));
+        return -2;
+    }
+    E.text_cap = cap;
+    return 0;
+}
+
+static int ensure_stage(size_t bytes, int slots)
+{
+    Engine &E = engine();
+    if (E.stage_bytes >= bytes && (int)E.stage.size() >= slots) return 0;
+    for (auto &s : E.stage)
+    {
+        cudaFreeHost(s.buf);
+        if (s.ev) cudaEventDestroy(s.ev);
+    }
+    E.stage.clear();
+    E.stage.resize(slots);
+    for (auto &s : E.stage)
+    {
+        CKH(cudaMallocHost(&s.buf, bytes));
+        CKH(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+        s.in_flight = false;
+    }
+    E.stage_bytes = bytes;
+    return 0;
+}
+
+static cudaEvent_t pool_event(size_t idx)
+{
+    Engine &E = engine();
+    while (E.ev_pool.size() <= idx)
+    {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        E.ev_pool.push_back(ev);
+    }
+    return E.ev_pool[idx];
+}
+
+static void parallel_copy(uint8_t *dst, const uint8_t *src, size_t n)
+{
+    const int nt = std::min(8, std::max(1, omp_get_max_threads()));
+    if (n < (8u << 20) || nt == 1)
+    {
+        memcpy(dst, src, n);
+        return;
+    }
+    const size_t piece = (n / nt + 4095) & ~(size_t)4095;
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int i = 0; i < nt; i++)
+    {
+        const size_t off = (size_t)i * piece;
+        if (off < n) memcpy(dst + off, src + off, std::min(piece, n - off));
+    }
+}
+
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Copies text[0..n) into E.d_text and scans it; on return *so describes the sorted device list.
+static int stage_and_scan(const Plan *plan, const char *text, size_t n, int want_positions, ScanOut *so)
+{
+    Engine &E = engine();
+    if (ensure_text(n) != 0) return -2;
+    if (want_positions && ensure_keys(1) != 0) return -2;
+    const uint32_t halo = (plan->is_ac ? plan->max_len : plan->m) + 1; // occurrence + the byte after it (-w)
+    const bool pinned = is_pinned(text);
+    const size_t chunk = pinned ? env_mb("KREP_B200_CHUNK_MB", 256) : env_mb("KREP_B200_STAGE_MB", 32);
+    krep_b200_shard_t sh;
+    sh.d_text = E.d_text;
+    sh.avail_len = n;
+    sh.own_begin = 0;
+    sh.own_end = n;
+    sh.global_offset = 0;
+    sh.prev_byte = -1;
+    sh.next_byte = -1;
+    if (n <= chunk + halo)
+    {
+        CKH(cudaMemcpyAsync(E.d_text, text, n, cudaMemcpyHostToDevice, E.scan_stream));
+        return scan_shard(plan, &sh, want_positions, E.scan_stream, so);
+    }
+    if (!pinned && ensure_stage(chunk, 3) != 0) return -2;
+    reset_kernel_ms();
+    if (reset_counter(E.scan_stream) != 0) return -2;
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    uint64_t scanned_to = 0; // starts < scanned_to are done
+    for (size_t c = 0; c < nchunks; c++)
+    {
+        const size_t off = c * chunk, len = std::min(chunk, n - off);
+        if (pinned)
+            CKH(cudaMemcpyAsync(E.d_text + off, text + off, len, cudaMemcpyHostToDevice, E.copy_stream));
+        else
+        {
+            StageSlot &s = E.stage[c % E.stage.size()];
+            if (s.in_flight) CKH(cudaEventSynchronize(s.ev));
+            parallel_copy(s.buf, (const uint8_t *)text + off, len);
+            CKH(cudaMemcpyAsync(E.d_text + off, s.buf, len, cudaMemcpyHostToDevice, E.copy_stream));
+            CKH(cudaEventRecord(s.ev, E.copy_stream));
+            s.in_flight = true;
+        }
+        cudaEvent_t landed = pool_event(3 * c);
+        CKH(cudaEventRecord(landed, E.copy_stream));
+        CKH(cudaStreamWaitEvent(E.scan_stream, landed, 0));
+        const bool last = c + 1 == nchunks;
+        const uint64_t resident = off + len;
+        krep_b200_shard_t part = sh;
+        part.avail_len = last ? n : resident; // never read bytes that have not landed yet
+        part.own_begin = scanned_to;
+        part.own_end = last ? n : (resident > halo ? resident - halo : 0);
+        part.next_byte = -1; // not needed: own_end leaves the following byte inside avail_len
+        if (part.own_end > part.own_begin)
+        {
+            cudaEvent_t a = pool_event(3 * c + 1), b = pool_event(3 * c + 2);
+            CKH(cudaEventRecord(a, E.scan_stream));
+            int rc = launch_scan(plan, &part, want_positions, E.scan_stream);
+            if (rc != 0) return rc;
+            CKH(cudaEventRecord(b, E.scan_stream));
+            scanned_to = part.own_end;
+        }
+    }
+    CKH(cudaGetLastError());
+    uint64_t cnt = 0;
+    if (read_counter(E.scan_stream, &cnt) != 0) return -2;
+    for (auto &s : E.stage) s.in_flight = false;
+    for (size_t c = 0; c < nchunks; c++)
+    {
+        float ms = 0.f;
+        if (3 * c + 2 < E.ev_pool.size() && cudaEventElapsedTime(&ms, E.ev_pool[3 * c + 1], E.ev_pool[3 * c + 2]) == cudaSuccess)
+            add_kernel_ms(ms);
+        else
+            cudaGetLastError();
+    }
+    so->count = cnt;
+    so->overflow = 0;
+    so->stored = 0;
+    so->d_keys = nullptr;
+    if (!want_positions) return 0;
+    if (cnt > E.key_cap)
+    {
+        // list overflowed: the text is resident now, rescan it in one launch with a large enough list
+        if (ensure_keys(cnt + cnt / 8 + 1024) != 0) return -2;
+        return scan_shard(plan, &sh, want_positions, E.scan_stream, so);
+    }
+    so->stored = cnt;
+    return sort_keys(cnt, key_end_bit(plan, n), E.scan_stream, &so->d_keys);
+}
+
+static int fetch_keys(const ScanOut &so, const uint64_t **h)
+{
+    Engine &E = engine();
+    *h = nullptr;
+    if (so.stored == 0) return 0;
+    if (so.stored > E.h_keys_cap)
+    {
+        cudaFreeHost(E.h_keys);
+        E.h_keys = nullptr;
+        E.h_keys_cap = 0;
+        uint64_t cap = std::max<uint64_t>(so.stored + so.stored / 4, 1 << 16);
+        CKH(cudaMallocHost(&E.h_keys, cap * sizeof(uint64_t)));
+        E.h_keys_cap = cap;
+    }
+    CKH(cudaMemcpyAsync(E.h_keys, so.d_keys, so.stored * sizeof(uint64_t), cudaMemcpyDeviceToHost, E.scan_stream));
+    CKH(cudaStreamSynchronize(E.scan_stream));
+    *h = E.h_keys;
+    return 0;
+}
+
+// Does the emulated kernel keep every (whole-word-valid) occurrence?  If so a bare count is enough.
+static bool keeps_all(int algo, bool only_matching, const search_params_t *P, const Plan *pl)
+{
+    if (pl->is_ac) return true;
+    if (pl->emit_len != pl->m) return false;
+    if (pl->border_free) return true; // occurrences cannot overlap: every overlap policy keeps all
+    switch (algo)
+    {
+    case KREP_B200_ALGO_BMH: return !(only_matching && !P->count_lines_mode);
+    case KREP_B200_ALGO_MEMCHR: return true;
+    case KREP_B200_ALGO_MEMCHR_SHORT: return !only_matching;
+    case KREP_B200_ALGO_SSE42: return only_matching;
+    default: return false;
+    }
+}
+
+// Return value of the emulated kernel when all `total` occurrences are kept and only the -m limit acts.
+static uint64_t limited_count(int algo, const search_params_t *P, uint64_t total)
+{
+    const uint64_t maxc = P->max_count;
+    switch (algo)
+    {
+    case KREP_B200_ALGO_BMH:
+    case KREP_B200_ALGO_MEMCHR_SHORT:
+        // count first, test afterwards (krep.c:1355-1367): with -m 0 in a pure count mode one match still counts
+        if (total == 0) return 0;
+        return maxc == 0 ? 1 : std::min<uint64_t>(total, maxc);
+    default:
+        return std::min<uint64_t>(total, maxc);
+    }
+}
+
+static uint64_t run_search(int entry_algo, const search_params_t *P, const char *text, size_t n, match_result_t *res)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    clear_error();
+    if (!P) return 0;
+    const bool only_matching = g_only_matching;
+    int algo = entry_algo;
+    size_t m = 0;
+    if (algo == KREP_B200_ALGO_AC)
+    {
+        if (!P->ac_trie || !text) return 0;  // aho_corasick.c:306
+        if (P->max_count == 0) return 0;     // aho_corasick.c:316
+        if (n == 0)                          // aho_corasick.c:442-463
+        {
+            for (size_t k = 0; k < P->num_patterns; k++)
+                if (P->pattern_lens[k] == 0)
+                {
+                    if (P->track_positions && res) result_push(res, 0, 0);
+                    return 1;
+                }
+            return 0;
+        }
+    }
+    else
+    {
+        algo = resolve_algo(P, algo);
+        m = P->pattern_len;
+        switch (algo)
+        {
+        case KREP_B200_ALGO_KMP:
+            if (P->max_count == 0) return 0;
+            if (m == 0 || n < m) return 0;
+            break;
+        case KREP_B200_ALGO_MEMCHR:
+            if (P->max_count == 0 || n == 0) return 0;
+            m = 1;
+            break;
+        case KREP_B200_ALGO_MEMCHR_SHORT:
+            if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
+            if (m < 2 || m > 3 || n < m) return 0;
+            break;
+        default: // BMH, SSE42 and the long simd entries
+            if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
+            if (m == 0 || n < m) return 0;
+            break;
+        }
+        if (!P->pattern) return 0;
+        if (m > 1024)
+        {
+            set_error(-3, "pattern longer than 1024 bytes (MAX_PATTERN_LENGTH, krep.c:77)");
+            return 0;
+        }
+    }
+    if (!engine_ok()) return 0;
+    Plan *plan = cached_plan(P, algo, only_matching);
+    if (!plan) return 0;
+    const bool want_result = P->track_positions && res;
+    const bool need_list = P->count_lines_mode || want_result || !keeps_all(algo, only_matching, P, plan) ||
+                           plan->whole_word == 2;
+    ScanOut so;
+    if (stage_and_scan(plan, text, n, need_list ? 1 : 0, &so) != 0) return 0;
+    if (!need_list) return limited_count(algo, P, so.count);
+    const uint64_t *keys = nullptr;
+    if (fetch_keys(so, &keys) != 0) return 0;
+    Replay r{keys, (size_t)so.stored, text, n, 0};
+    if (plan->is_ac) return replay_ac(P, r, res);
+    return replay_literal(algo, P, only_matching, plan->m, r, res);
+}
+
+} // namespace kb
+
+using namespace kb;
+
+extern "C" {
+
+void krep_b200_set_only_matching(bool on) { g_only_matching = on; }
+bool krep_b200_get_only_matching(void) { return g_only_matching; }
+void krep_b200_set_force_no_simd(bool on) { g_force_no_simd = on; }
+void krep_b200_set_algo_override(const char *name) { g_algo_override = name ? name : ""; }
+
+uint64_t krep_b200_boyer_moore_search(const search_params_t *p, const char *t, size_t n, match_result_t *r)
+{
+    return run_search(KREP_B200_ALGO_BMH, p, t, n, r);
+}
+uint64_t krep_b200_kmp_search(const search_params_t *p, const char *t, size_t n, match_result_t *r)
+{
+    return run_search(KREP_B200_ALGO_KMP, p, t, n, r);
+}
+uint64_t krep_b200_memchr_search(const search_params_t *p, const char *t, size_t n, match_result_t *r)
+{
+    return run_search(KREP_B200_ALGO_MEMCHR, p, t, n, r);
+}
+uint64_t krep_b200_memchr_short_search(const search_params_t *p, const char *t, size_t n, match_result_t *r)
+{
+    return run_search(KREP_B200_ALGO_MEMCHR_SHORT, p, t, n, r);
+}
+uint64_t krep_b200_simd_sse42_search(const search_params_t *p, const char *t, size_t n, match_result_t *r)
+{
+    return run_search(KREP_B200_ALGO_SSE42, p, t, n, r);
+}
+uint64_t krep_b200_simd_avx2_search(const search_params_t *p, const char *t, size_t n, match_result_t *r)
+{
+    return run_search(KREP_B200_ALGO_AVX2, p, t, n, r);
+}
+uint64_t krep_b200_simd_avx512_search(const search_params_t *p, const char *t, size_t n, match_result_t *r)
+{
+    return run_search(KREP_B200_ALGO_AVX512, p, t, n, r);
+}
+uint64_t krep_b200_aho_corasick_search(const search_params_t *p, const char *t, size_t n, match_result_t *r)
+{
+    return run_search(KREP_B200_ALGO_AC, p, t, n, r);
+}
+
+// krep.c:1873-1914
+static bool is_repetitive_pattern(const char *pattern, size_t len)
+{
+    if (len < 3) return false;
+    size_t run = 0;
+    char prev = pattern[0];
+    for (size_t i = 1; i < len; i++)
+    {
+        if (pattern[i] == prev)
+        {
+            if (++run >= len / 2) return true;
+        }
+        else
+        {
+            run = 0;
+            prev = pattern[i];
+        }
+    }
+    for (size_t period = 2; period <= len / 2; period++)
+    {
+        bool periodic = true;
+        for (size_t i = period; i < len && periodic; i++) periodic = pattern[i] == pattern[i % period];
+        if (periodic) return true;
+    }
+    return false;
+}
+
+// krep.c:1771-1870, for the AVX2 build of the reference (SIMD_MAX_PATTERN_LEN 32).
+search_func_t krep_b200_select_search_algorithm(const search_params_t *P)
+{
+    if (!P || P->use_regex) return NULL; // regex stays with the host's regex_search
+    if (P->num_patterns > 1) return krep_b200_aho_corasick_search;
+    if (!g_algo_override.empty() && g_algo_override != "auto")
+    {
+        if (g_algo_override == "bm") return krep_b200_boyer_moore_search;
+        if (g_algo_override == "kmp") return krep_b200_kmp_search;
+    }
+    const size_t m = P->pattern_len;
+    const bool can_simd = !g_force_no_simd && m <= SIMD_MAX_PATTERN_LEN;
+    if (m == 1) return krep_b200_memchr_search;
+    if (m < 4) return (can_simd && P->case_sensitive) ? krep_b200_simd_avx2_search : krep_b200_memchr_short_search;
+    if (can_simd && m <= 32) return krep_b200_simd_avx2_search;
+    if (m < 8 && is_repetitive_pattern(P->pattern, m)) return krep_b200_kmp_search;
+    return krep_b200_boyer_moore_search;
+}
+
+const char *krep_b200_get_algorithm_name(search_func_t f)
+{
+    if (f == krep_b200_boyer_moore_search) return "Boyer-Moore-Horspool";
+    if (f == krep_b200_kmp_search) return "Knuth-Morris-Pratt";
+    if (f == krep_b200_aho_corasick_search) return "Aho-Corasick";
+    if (f == krep_b200_memchr_search) return "memchr";
+    if (f == krep_b200_memchr_short_search) return "memchr-short";
+    if (f == krep_b200_simd_sse42_search) return "SSE4.2";
+    if (f == krep_b200_simd_avx2_search) return "AVX2";
+    if (f == krep_b200_simd_avx512_search) return "AVX-512";
+    return "Unknown";
+}
+
+// ---- AC trie handles (aho_corasick.c:111 / 274 / 287) ----
+ac_trie_t *krep_b200_ac_trie_build(const search_params_t *params)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    clear_error();
+    if (!params || params->num_patterns == 0) return NULL; // aho_corasick.c:113
+    if (!engine_ok()) return NULL;
+    return reinterpret_cast<ac_trie_t *>(cached_plan(params, KREP_B200_ALGO_AC, false));
+}
+void krep_b200_ac_trie_free(ac_trie_t *) { /* plans are owned by the engine's cache */ }
+bool krep_b200_ac_trie_root_has_outputs(const ac_trie_t *trie)
+{
+    const Plan *pl = reinterpret_cast<const Plan *>(trie);
+    if (!pl || pl->magic != 0x6b7265705f623230ull || !pl->is_ac) return false;
+    for (uint32_t len : pl->pat_lens)
+        if (len == 0) return true; // an empty pattern's index sits on the root (aho_corasick.c:145)
+    return false;
+}
+
+// ---- match_result helpers (krep.c:139 / 175 / 244 / 256) ----
+match_result_t *krep_b200_match_result_init(uint64_t initial_capacity)
+{
+    match_result_t *r = (match_result_t *)malloc(sizeof *r);
+    if (!r) return NULL;
+    if (initial_capacity == 0) initial_capacity = 16;
+    if (initial_capacity > SIZE_MAX / sizeof(match_position_t))
+    {
+        free(r);
+        return NULL;
+    }
+    r->positions = (match_position_t *)malloc(initial_capacity * sizeof(match_position_t));
+    if (!r->positions)
+    {
+        free(r);
+        return NULL;
+    }
+    r->count = 0;
+    r->capacity = initial_capacity;
+    return r;
+}
+bool krep_b200_match_result_add(match_result_t *r, size_t s, size_t e) { return result_push(r, s, e); }
+void krep_b200_match_result_free(match_result_t *r)
+{
+    if (!r) return;
+    free(r->positions);
+    free(r);
+}
+bool krep_b200_match_result_merge(match_result_t *dest, const match_result_t *src, size_t chunk_offset)
+{
+    if (!dest || !src || src->count == 0) return true;
+    for (uint64_t i = 0; i < src->count; i++)
+        if (!result_push(dest, src->positions[i].start_offset + chunk_offset, src->positions[i].end_offset + chunk_offset))
+            return false;
+    return true;
+}
+
+uint64_t krep_b200_replay(int algo, const search_params_t *P, bool only_matching, const uint64_t *keys, uint64_t nkeys,
+                          const char *text, size_t text_len, match_result_t *result)
+{
+    if (!P) return 0;
+    if (P->count_lines_mode && !text && nkeys)
+    {
+        set_error(-3, "krep_b200_replay: -c line counting needs the host text");
+        return 0;
+    }
+    Replay r{keys, (size_t)nkeys, text, text ? text_len : (SIZE_MAX >> 1), 0};
+    if (algo == KREP_B200_ALGO_AC) return replay_ac(P, r, result);
+    algo = resolve_algo(P, algo);
+    const uint32_t m = algo == KREP_B200_ALGO_MEMCHR ? 1u : (uint32_t)P->pattern_len;
+    return replay_literal(algo, P, only_matching, m, r, result);
+}
+
+// ---- shard result -> match_result_t under the emulated kernel's policy ----
+uint64_t krep_b200_collect(const krep_b200_plan_t *plan_, const search_params_t *P, const krep_b200_device_result_t *dev,
+                           match_result_t *result)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    clear_error();
+    const Plan *plan = reinterpret_cast<const Plan *>(plan_);
+    if (!plan || !P || !dev) return 0;
+    if (P->count_lines_mode)
+    {
+        set_error(-3, "krep_b200_collect: -c line counting needs host text; use the search_func_t entry points");
+        return 0;
+    }
+    ScanOut so;
+    so.count = dev->count;
+    so.stored = dev->stored;
+    so.d_keys = dev->d_keys;
+    const uint64_t *keys = nullptr;
+    if (so.stored && fetch_keys(so, &keys) != 0) return 0;
+    if (!so.stored) return limited_count(plan->algo, P, plan->is_ac || keeps_all(plan->algo, g_only_matching, P, plan) ? so.count : 0);
+    Replay r{keys, (size_t)so.stored, nullptr, SIZE_MAX >> 1, 0};
+    if (plan->is_ac) return replay_ac(P, r, result);
+    return replay_literal(plan->algo, P, plan->built_only_matching, plan->m, r, result);
+}
+
+} // extern "C"

@@ -1,0 +1,277 @@
+// scan_literal.cu — single-literal scan kernels for sm_100a.
+//
+// Replaces the inner loops of boyer_moore_search (krep.c:1294-1382), kmp_search (krep.c:1663-1763),
+// memchr_search / memchr_short_search (krep.c:3918-4023, 4396-4500) and the simd_* searches
+// (krep.c:4737-4866, 4914-5056, 5145-5255).  All of those enumerate the occurrences of one literal;
+// they differ only in which occurrences they keep afterwards (overlap policy, -w, -c, -m), which
+// semantics.cpp replays over the sorted occurrence list.  So the device work is one thing:
+// emit every position where the literal occurs, exactly once, at HBM speed.
+//
+// Design (HBM-bound byte scan, no tensor cores — nothing here is a contraction):
+//   * every thread streams 16-byte vectors (LDG.128, coalesced: a warp reads 512 contiguous bytes),
+//     UNROLL vectors in flight per thread; the grid is sized to the SM count x resident CTAs and walks
+//     the shard with a grid stride, so neighbouring CTAs read neighbouring DRAM pages;
+//   * the hot loop only FILTERS, with ~1 integer op per corpus byte:
+//       ALIGNED4 (pattern_len >= 7): an occurrence at p fully contains the aligned word j = ceil(p/4),
+//         which then equals P[d..d+4) with d = 4j-p in 0..3.  Each aligned text word is compared with
+//         those four constants — no halo, no shuffles, no shared memory; case-insensitive search ANDs
+//         the word with 0xDFDFDFDF first (a superset filter: folds letters exactly, aliases a few
+//         punctuation bytes, verified exactly afterwards);
+//       WINDOW4 (pattern_len < 7): the 4-byte window at every byte offset, built with funnel shifts from
+//         the thread's own words plus the first word of the next vector, is compared with P[0..4) under a
+//         length mask;
+//   * a thread whose vector contains a candidate (rare) calls the out-of-line verifier, which compares
+//     all pattern bytes under the exact per-byte case mask, evaluates the whole-word boundary against the
+//     global text (shard context bytes at the edges, so results equal the reference's single-chunk run,
+//     SURVEY §8 a12), checks shard ownership by start offset and appends one 64-bit key.
+//
+// Algorithmic traffic: 1 byte read per corpus byte (+ 8 B written per occurrence).
+#include "common.h"
+
+namespace kb {
+
+__device__ __forceinline__ bool dev_is_word(int c)
+{
+    return (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_';
+}
+
+// Exact check of one candidate start + emission. Out of line on purpose: keeps the streaming loop's
+// register footprint small; executed for a vanishing fraction of positions on low-hit-rate corpora.
+// Returns 1 when the occurrence was only counted (count-only launch), else 0.
+__device__ __noinline__ unsigned verify_emit(const LitDevParams &p, long long cand)
+{
+    if (cand < (long long)p.own_begin || cand >= (long long)p.own_end) return 0;
+    const uint64_t c = (uint64_t)cand;
+    if (c + p.emit_len > p.avail_len) return 0;
+    const uint8_t *t = p.text + c;
+    const uint8_t *val = p.pat_val, *msk = p.pat_mask;
+    for (uint32_t k = 0; k < p.emit_len; k++)
+        if ((t[k] & msk[k]) != val[k]) return 0;
+    unsigned full = 1;
+    if (p.m > p.emit_len)
+    {
+        if (c + p.m > p.avail_len) full = 0;
+        else
+            for (uint32_t k = p.emit_len; k < p.m; k++)
+                if ((t[k] & msk[k]) != val[k]) { full = 0; break; }
+    }
+    unsigned ww_ok = 1;
+    if (p.whole_word)
+    {
+        const uint64_t e = c + p.m;
+        const int pb = c > 0 ? (int)t[-1] : p.prev_byte;
+        const int nb = e < p.avail_len ? (int)p.text[e] : p.next_byte;
+        ww_ok = !(dev_is_word(pb) || dev_is_word(nb));
+        if (p.whole_word == 1 && !ww_ok) return 0;
+    }
+    if (p.want_positions)
+    {
+        const unsigned long long slot = atomicAdd(p.counter, 1ULL);
+        if (slot < p.cap) p.out[slot] = ((p.global_offset + c) << LIT_TAG_BITS) | (full << 1) | ww_ok;
+        return 0;
+    }
+    return 1;
+}
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *ptr)
+{
+    return __ldcs(ptr); // ld.global.cs: streamed once, evict-first
+}
+
+// ------------------------------------------------------------------------------------ ALIGNED4
+template <bool FOLD>
+__device__ __forceinline__ bool hit_word(uint32_t w, uint32_t fold, uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3)
+{
+    if (FOLD) w &= fold;
+    return (w == k0) | (w == k1) | (w == k2) | (w == k3);
+}
+template <bool FOLD>
+__device__ __forceinline__ bool hit_vec(const uint4 &v, uint32_t fold, uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3)
+{
+    return hit_word<FOLD>(v.x, fold, k0, k1, k2, k3) | hit_word<FOLD>(v.y, fold, k0, k1, k2, k3) |
+           hit_word<FOLD>(v.z, fold, k0, k1, k2, k3) | hit_word<FOLD>(v.w, fold, k0, k1, k2, k3);
+}
+
+__device__ __noinline__ unsigned slow_aligned4(const LitDevParams &p, uint64_t group, uint4 v)
+{
+    unsigned n = 0;
+    const uint32_t w[4] = {v.x & p.fold, v.y & p.fold, v.z & p.fold, v.w & p.fold};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int d = 0; d < 4; d++)
+            if (w[k] == p.K[d]) n += verify_emit(p, (long long)(group * 16 + 4 * k) - d);
+    return n;
+}
+
+__device__ __forceinline__ void tail_and_count(const LitDevParams &p, unsigned long long local_cnt)
+{
+    if (blockIdx.x == 0 && threadIdx.x < 32 && p.avail_len >= p.emit_len)
+    {
+        const uint64_t last = p.avail_len - p.emit_len;
+        for (uint64_t s = p.tail_start + threadIdx.x; s <= last; s += 32) local_cnt += verify_emit(p, (long long)s);
+    }
+    if (!p.want_positions)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local_cnt += __shfl_xor_sync(0xffffffffu, local_cnt, o);
+        if ((threadIdx.x & 31) == 0 && local_cnt) atomicAdd(p.counter, local_cnt);
+    }
+}
+
+template <bool FOLD, int UNROLL>
+__global__ void __launch_bounds__(256, 4) k_lit_aligned4(const __grid_constant__ LitDevParams p)
+{
+    const uint4 *__restrict__ t4 = reinterpret_cast<const uint4 *>(p.text);
+    const uint32_t k0 = p.K[0], k1 = p.K[1], k2 = p.K[2], k3 = p.K[3], fold = p.fold;
+    unsigned long long local_cnt = 0;
+    const uint64_t tile = (uint64_t)blockDim.x * UNROLL;
+    const uint64_t stride = (uint64_t)gridDim.x * tile;
+    uint64_t g0 = p.group_begin + (uint64_t)blockIdx.x * tile;
+    for (; g0 + tile <= p.group_end; g0 += stride)
+    {
+        uint4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) v[u] = ld_stream(t4 + g0 + (uint64_t)u * blockDim.x + threadIdx.x);
+        bool hit = false;
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) hit |= hit_vec<FOLD>(v[u], fold, k0, k1, k2, k3);
+        if (hit)
+        {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++)
+                if (hit_vec<FOLD>(v[u], fold, k0, k1, k2, k3))
+                    local_cnt += slow_aligned4(p, g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u]);
+        }
+    }
+    if (g0 < p.group_end) // the one ragged tile
+    {
+        for (int u = 0; u < UNROLL; u++)
+        {
+            const uint64_t g = g0 + (uint64_t)u * blockDim.x + threadIdx.x;
+            if (g < p.group_end)
+            {
+                const uint4 v = ld_stream(t4 + g);
+                if (hit_vec<FOLD>(v, fold, k0, k1, k2, k3)) local_cnt += slow_aligned4(p, g, v);
+            }
+        }
+    }
+    tail_and_count(p, local_cnt);
+}
+
+// ------------------------------------------------------------------------------------ WINDOW4
+__device__ __forceinline__ bool hit_pair(uint32_t lo, uint32_t hi, uint32_t mask, uint32_t k0)
+{
+    return ((lo & mask) == k0) | ((__funnelshift_r(lo, hi, 8) & mask) == k0) |
+           ((__funnelshift_r(lo, hi, 16) & mask) == k0) | ((__funnelshift_r(lo, hi, 24) & mask) == k0);
+}
+__device__ __forceinline__ bool hit_vec_w(const uint4 &v, uint32_t nx, uint32_t mask, uint32_t k0)
+{
+    return hit_pair(v.x, v.y, mask, k0) | hit_pair(v.y, v.z, mask, k0) | hit_pair(v.z, v.w, mask, k0) |
+           hit_pair(v.w, nx, mask, k0);
+}
+
+__device__ __noinline__ unsigned slow_window4(const LitDevParams &p, uint64_t group, uint4 v, uint32_t nx)
+{
+    unsigned n = 0;
+    const uint32_t w[5] = {v.x, v.y, v.z, v.w, nx};
+    const uint32_t mask = p.fold & p.win_mask, k0 = p.K[0];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            const uint32_t win = r == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * r);
+            if ((win & mask) == k0) n += verify_emit(p, (long long)(group * 16 + 4 * k + r));
+        }
+    return n;
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ LitDevParams p)
+{
+    const uint4 *__restrict__ t4 = reinterpret_cast<const uint4 *>(p.text);
+    const uint32_t mask = p.fold & p.win_mask, k0 = p.K[0];
+    unsigned long long local_cnt = 0;
+    const uint64_t tile = (uint64_t)blockDim.x * UNROLL;
+    const uint64_t stride = (uint64_t)gridDim.x * tile;
+    uint64_t g0 = p.group_begin + (uint64_t)blockIdx.x * tile;
+    for (; g0 + tile <= p.group_end; g0 += stride)
+    {
+        uint4 v[UNROLL];
+        uint32_t nx[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+        {
+            const uint4 *q = t4 + g0 + (uint64_t)u * blockDim.x + threadIdx.x;
+            v[u] = ld_stream(q);
+            nx[u] = __ldg(reinterpret_cast<const uint32_t *>(q + 1)); // first word of the next vector (L1/L2 hit)
+        }
+        bool hit = false;
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) hit |= hit_vec_w(v[u], nx[u], mask, k0);
+        if (hit)
+        {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++)
+                if (hit_vec_w(v[u], nx[u], mask, k0))
+                    local_cnt += slow_window4(p, g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u], nx[u]);
+        }
+    }
+    if (g0 < p.group_end)
+    {
+        for (int u = 0; u < UNROLL; u++)
+        {
+            const uint64_t g = g0 + (uint64_t)u * blockDim.x + threadIdx.x;
+            if (g < p.group_end)
+            {
+                const uint4 v = ld_stream(t4 + g);
+                const uint32_t nx = __ldg(reinterpret_cast<const uint32_t *>(t4 + g + 1));
+                if (hit_vec_w(v, nx, mask, k0)) local_cnt += slow_window4(p, g, v, nx);
+            }
+        }
+    }
+    tail_and_count(p, local_cnt);
+}
+
+// ------------------------------------------------------------------------------------ launch
+static int g_sm_count = 0;
+static int g_occ[3] = {0, 0, 0};
+
+template <typename K>
+static int occupancy(K kernel)
+{
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, 0);
+    return nb > 0 ? nb : 1;
+}
+
+void launch_literal(const Plan *plan, const LitDevParams &p, cudaStream_t s)
+{
+    constexpr int UNROLL = 4;
+    if (!g_sm_count)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        g_occ[0] = occupancy(k_lit_aligned4<false, UNROLL>);
+        g_occ[1] = occupancy(k_lit_aligned4<true, UNROLL>);
+        g_occ[2] = occupancy(k_lit_window4<UNROLL>);
+    }
+    const uint64_t groups = p.group_end > p.group_begin ? p.group_end - p.group_begin : 0;
+    const uint64_t tile = 256ull * UNROLL;
+    uint64_t tiles = (groups + tile - 1) / tile;
+    if (tiles == 0) tiles = 1; // still need the tail warp
+    const int which = plan->filter == FILTER_WINDOW4 ? 2 : (plan->fold != 0xFFFFFFFFu ? 1 : 0);
+    uint64_t resident = (uint64_t)g_sm_count * g_occ[which];
+    const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
+    if (which == 2)
+        k_lit_window4<UNROLL><<<grid, 256, 0, s>>>(p);
+    else if (which == 1)
+        k_lit_aligned4<true, UNROLL><<<grid, 256, 0, s>>>(p);
+    else
+        k_lit_aligned4<false, UNROLL><<<grid, 256, 0, s>>>(p);
+    count_launch();
+}
+
+} // namespace kb

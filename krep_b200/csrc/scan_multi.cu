@@ -1,0 +1,397 @@
+// scan_multi.cu — multi-pattern scan for sm_100a; replaces aho_corasick_search's per-byte goto/fail
+// walk (aho_corasick.c:328-437) and ac_trie_build (aho_corasick.c:111-271).
+//
+// The reference chases pointers through 2 KB trie nodes, one dependent load per text byte.  A GPU at
+// HBM speed cannot afford a serial automaton, so the same result set — every occurrence of every
+// pattern, nested and overlapping ones included, duplicates in the pattern list emitted once per
+// index (aho_corasick.c:361) — is produced by filter + verify instead:
+//
+//   * SAMPLED WINDOW FILTER.  With Lmin the shortest pattern, pick a window width w and a sampling
+//     stride s in {1,2,4} with w + s - 1 <= Lmin.  Every occurrence starting at p then contains the
+//     w-byte window at a = ceil(p/s)*s, which equals bytes [d, d+w) of its pattern with d = a-p < s.
+//     All s*K such pattern windows are hashed into a bitmap of 2^B bits that lives in SHARED MEMORY
+//     (up to 128 KB of the SM's 227 KB); the hot loop hashes the text window at every multiple of s
+//     and tests one bit.  Text is streamed exactly once with coalesced 16-byte loads.
+//   * EXACT WINDOW TABLE (L2-resident, open addressing) maps a window value that passed the bitmap to
+//     its list of (pattern, d) pairs — this kills bitmap false positives in ~one L2 load;
+//   * VERIFY compares the whole pattern at p = a - d under the exact per-byte case mask, applies the
+//     whole-word test against the global text, shard ownership by start offset, and emits one key
+//     (end << 24 | (1023 - (len-1)) << 14 | pattern_index) whose ascending order is
+//     aho_corasick_search's emission order (end ascending, longest first, list order).
+//
+// Case-insensitive search hashes (text & 0xDF..DF) against equally folded pattern windows (a superset
+// filter); the verify step is exact, equal to lower_table on both sides (aho_corasick.c:161, 333).
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+#include "common.h"
+
+namespace kb {
+
+struct AcSlot
+{
+    uint64_t key; // folded window value (low w bytes)
+    uint32_t first, count;
+};
+
+struct AcDevTables
+{
+    uint32_t *d_bitmap = nullptr; // 2^B bits
+    AcSlot *d_slots = nullptr;    // nslots (power of two)
+    uint32_t *d_list = nullptr;   // (pattern << 2) | d
+    uint8_t *d_pool_val = nullptr, *d_pool_mask = nullptr;
+    uint32_t *d_pat_off = nullptr, *d_pat_len = nullptr;
+    uint32_t B = 0, nslots = 0, w = 0, s = 0, npat = 0;
+    uint64_t wmask = 0; // low w bytes
+    uint32_t fold = 0xFFFFFFFFu;
+};
+
+struct AcDev
+{
+    const uint32_t *bitmap;
+    const AcSlot *slots;
+    const uint32_t *list;
+    const uint8_t *pool_val, *pool_mask;
+    const uint32_t *pat_off, *pat_len;
+    uint32_t B, nslots, w, npat;
+    uint32_t wmask_lo, wmask_hi, fold;
+    // launch
+    const uint8_t *text;
+    uint64_t avail_len, own_begin, own_end, global_offset;
+    int32_t prev_byte, next_byte;
+    uint64_t group_begin, group_end, tail_a; // occurrences whose sampled window position is >= tail_a go to the tail warp
+    uint64_t *out;
+    uint64_t cap;
+    unsigned long long *counter;
+    uint32_t whole_word, want_positions;
+};
+
+static constexpr uint32_t HC1 = 0x9E3779B1u, HC2 = 0x85EBCA77u;
+
+__host__ __device__ __forceinline__ uint32_t win_hash(uint32_t lo, uint32_t hi) { return lo * HC1 + hi * HC2; }
+__host__ __device__ __forceinline__ uint32_t slot_hash(uint32_t lo, uint32_t hi)
+{
+    uint32_t h = (lo ^ (hi * 0xC2B2AE3Du)) * 0x27D4EB2Fu;
+    return h ^ (h >> 15);
+}
+
+__device__ __forceinline__ bool dev_is_word2(int c)
+{
+    return (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_';
+}
+
+// exact check of pattern k at start p (p may be negative / out of range) + emission
+__device__ __noinline__ unsigned ac_verify_emit(const AcDev &A, uint32_t k, long long cand)
+{
+    if (cand < (long long)A.own_begin || cand >= (long long)A.own_end) return 0;
+    const uint64_t p = (uint64_t)cand;
+    const uint32_t len = A.pat_len[k];
+    if (len == 0 || p + len > A.avail_len) return 0;
+    const uint8_t *t = A.text + p;
+    const uint8_t *val = A.pool_val + A.pat_off[k], *msk = A.pool_mask + A.pat_off[k];
+    for (uint32_t i = 0; i < len; i++)
+        if ((t[i] & msk[i]) != val[i]) return 0;
+    if (A.whole_word)
+    {
+        const uint64_t e = p + len;
+        const int pb = p > 0 ? (int)t[-1] : A.prev_byte;
+        const int nb = e < A.avail_len ? (int)A.text[e] : A.next_byte;
+        if (dev_is_word2(pb) || dev_is_word2(nb)) return 0;
+    }
+    if (A.want_positions)
+    {
+        const unsigned long long slot = atomicAdd(A.counter, 1ULL);
+        if (slot < A.cap)
+            A.out[slot] = ((A.global_offset + p + len) << AC_END_SHIFT) | ((uint64_t)(1023u - (len - 1)) << AC_LEN_SHIFT) | k;
+        return 0;
+    }
+    return 1;
+}
+
+// window value (lo,hi already folded+masked) at sampled position a passed the bitmap
+__device__ __noinline__ unsigned ac_slow(const AcDev &A, uint64_t a, uint32_t lo, uint32_t hi)
+{
+    const uint64_t key = ((uint64_t)hi << 32) | lo;
+    uint32_t h = slot_hash(lo, hi) & (A.nslots - 1);
+    unsigned n = 0;
+    for (;;)
+    {
+        const AcSlot sl = A.slots[h];
+        if (sl.count == 0) return n;
+        if (sl.key == key)
+        {
+            for (uint32_t i = 0; i < sl.count; i++)
+            {
+                const uint32_t e = A.list[sl.first + i];
+                n += ac_verify_emit(A, e >> 2, (long long)a - (long long)(e & 3));
+            }
+            return n;
+        }
+        h = (h + 1) & (A.nslots - 1);
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(512, 1) k_ac_scan(const __grid_constant__ AcDev A)
+{
+    extern __shared__ uint32_t s_bitmap[];
+    {
+        const uint32_t words = 1u << (A.B - 5);
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.bitmap);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_bitmap);
+        for (uint32_t i = threadIdx.x; i < words / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint4 *__restrict__ t4 = reinterpret_cast<const uint4 *>(A.text);
+    const uint32_t fold = A.fold, mlo = A.wmask_lo & fold, mhi = A.wmask_hi & fold, shift = 32 - A.B;
+    unsigned long long local_cnt = 0;
+    for (uint64_t g = A.group_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.group_end;
+         g += (uint64_t)gridDim.x * blockDim.x)
+    {
+        const uint4 v = __ldcs(t4 + g);
+        const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(t4 + g + 1)); // 8 bytes after the vector (in bounds by group_end)
+        const uint32_t w[6] = {v.x, v.y, v.z, v.w, nx.x, nx.y};
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int r = 0; r < 4; r += S)
+            {
+                const uint32_t lo = (r == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * r)) & mlo;
+                const uint32_t hi = (r == 0 ? w[k + 1] : __funnelshift_r(w[k + 1], w[k + 2], 8 * r)) & mhi;
+                const uint32_t idx = win_hash(lo, hi) >> shift;
+                any |= (s_bitmap[idx >> 5] >> (idx & 31)) & 1u;
+            }
+        if (any)
+        {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int r = 0; r < 4; r += S)
+                {
+                    const uint32_t lo = (r == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * r)) & mlo;
+                    const uint32_t hi = (r == 0 ? w[k + 1] : __funnelshift_r(w[k + 1], w[k + 2], 8 * r)) & mhi;
+                    const uint32_t idx = win_hash(lo, hi) >> shift;
+                    if ((s_bitmap[idx >> 5] >> (idx & 31)) & 1u) local_cnt += ac_slow(A, g * 16 + 4 * k + r, lo, hi);
+                }
+        }
+    }
+    // tail: occurrences whose sampled window lies beyond the vector loop — brute force, lanes over patterns
+    if (blockIdx.x == 0 && threadIdx.x < 32)
+    {
+        const uint64_t first = A.tail_a >= (uint64_t)(S - 1) ? A.tail_a - (S - 1) : 0;
+        for (uint64_t p = first; p < A.avail_len; p++)
+        {
+            const uint64_t a = (p + S - 1) / S * S;
+            if (a < A.tail_a) continue;
+            for (uint32_t k = threadIdx.x; k < A.npat; k += 32) local_cnt += ac_verify_emit(A, k, (long long)p);
+        }
+    }
+    if (!A.want_positions)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local_cnt += __shfl_xor_sync(0xffffffffu, local_cnt, o);
+        if ((threadIdx.x & 31) == 0 && local_cnt) atomicAdd(A.counter, local_cnt);
+    }
+}
+
+// ------------------------------------------------------------------------------------- build
+static uint64_t pat_window(const uint8_t *p, uint32_t w, uint32_t fold)
+{
+    uint32_t lo = 0, hi = 0;
+    for (uint32_t i = 0; i < w; i++)
+    {
+        if (i < 4) lo |= (uint32_t)p[i] << (8 * i);
+        else hi |= (uint32_t)p[i] << (8 * (i - 4));
+    }
+    return ((uint64_t)(hi & fold) << 32) | (lo & fold);
+}
+
+#define CKB(call)                                                            \
+    do                                                                       \
+    {                                                                        \
+        if ((call) != cudaSuccess)                                           \
+        {                                                                    \
+            set_error(-2, "CUDA allocation/copy failed building AC tables"); \
+            ac_free_tables(plan);                                            \
+            return -2;                                                       \
+        }                                                                    \
+    } while (0)
+
+int ac_build_tables(Plan *plan)
+{
+    AcDevTables *T = new AcDevTables();
+    plan->ac = T;
+    const uint32_t K = (uint32_t)plan->patterns.size();
+    T->npat = K;
+    uint32_t lmin = 0xFFFFFFFFu, lmax = 0;
+    for (uint32_t k = 0; k < K; k++)
+    {
+        const uint32_t len = plan->pat_lens[k];
+        if (len == 0) continue; // empty patterns never match during the scan (aho_corasick.c:374)
+        lmin = std::min(lmin, len);
+        lmax = std::max(lmax, len);
+    }
+    if (lmax == 0) lmin = 0;
+    plan->min_len = lmin;
+    plan->max_len = lmax;
+    uint32_t w, s;
+    if (lmin >= 11) { w = 8; s = 4; }
+    else if (lmin >= 7) { w = lmin - 3; s = 4; }
+    else if (lmin >= 5) { w = lmin - 1; s = 2; }
+    else { w = lmin ? lmin : 1; s = 1; }
+    T->w = w;
+    T->s = s;
+    T->wmask = w >= 8 ? ~0ull : ((1ull << (8 * w)) - 1);
+    T->fold = plan->case_sensitive ? 0xFFFFFFFFu : 0xDFDFDFDFu;
+
+    // pattern pool (exact compare data) + window entries
+    std::vector<uint32_t> off(K), len(K);
+    std::vector<uint8_t> pv, pm;
+    struct Ent { uint64_t key; uint32_t e; };
+    std::vector<Ent> ents;
+    for (uint32_t k = 0; k < K; k++)
+    {
+        off[k] = (uint32_t)pv.size();
+        len[k] = plan->pat_lens[k];
+        const uint8_t *pb = (const uint8_t *)plan->patterns[k].data();
+        for (uint32_t i = 0; i < len[k]; i++)
+        {
+            const uint8_t m = (!plan->case_sensitive && is_alpha_c(pb[i])) ? 0xDF : 0xFF;
+            pm.push_back(m);
+            pv.push_back(pb[i] & m);
+        }
+        if (len[k] == 0) continue;
+        for (uint32_t d = 0; d < s; d++) ents.push_back({pat_window(pb + d, w, T->fold) & T->wmask, (k << 2) | d});
+    }
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.key < b.key; });
+    size_t distinct = 0;
+    for (size_t i = 0; i < ents.size(); i++)
+        if (i == 0 || ents[i].key != ents[i - 1].key) distinct++;
+    // bitmap size: keep the false-positive rate of one lookup around 0.2 % or better, 16 KB .. 128 KB
+    uint32_t B = 17;
+    while (B < 20 && (double)distinct / (double)(1u << B) > 0.002) B++;
+    T->B = B;
+    std::vector<uint32_t> bitmap(1u << (B - 5), 0);
+    uint32_t nslots = 16;
+    while (nslots < 2 * distinct + 1) nslots *= 2;
+    T->nslots = nslots;
+    std::vector<AcSlot> slots(nslots, AcSlot{0, 0, 0});
+    std::vector<uint32_t> list(ents.size());
+    for (size_t i = 0; i < ents.size();)
+    {
+        size_t j = i;
+        while (j < ents.size() && ents[j].key == ents[i].key) { list[j] = ents[j].e; j++; }
+        const uint32_t lo = (uint32_t)ents[i].key, hi = (uint32_t)(ents[i].key >> 32);
+        const uint32_t idx = win_hash(lo, hi) >> (32 - B);
+        bitmap[idx >> 5] |= 1u << (idx & 31);
+        uint32_t h = slot_hash(lo, hi) & (nslots - 1);
+        while (slots[h].count) h = (h + 1) & (nslots - 1);
+        slots[h] = AcSlot{ents[i].key, (uint32_t)i, (uint32_t)(j - i)};
+        i = j;
+    }
+    if (pv.empty()) { pv.push_back(0); pm.push_back(0); }
+    if (list.empty()) list.push_back(0);
+    CKB(cudaMalloc(&T->d_bitmap, bitmap.size() * 4));
+    CKB(cudaMalloc(&T->d_slots, slots.size() * sizeof(AcSlot)));
+    CKB(cudaMalloc(&T->d_list, list.size() * 4));
+    CKB(cudaMalloc(&T->d_pool_val, pv.size()));
+    CKB(cudaMalloc(&T->d_pool_mask, pm.size()));
+    CKB(cudaMalloc(&T->d_pat_off, (K ? K : 1) * 4));
+    CKB(cudaMalloc(&T->d_pat_len, (K ? K : 1) * 4));
+    CKB(cudaMemcpy(T->d_bitmap, bitmap.data(), bitmap.size() * 4, cudaMemcpyHostToDevice));
+    CKB(cudaMemcpy(T->d_slots, slots.data(), slots.size() * sizeof(AcSlot), cudaMemcpyHostToDevice));
+    CKB(cudaMemcpy(T->d_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice));
+    CKB(cudaMemcpy(T->d_pool_val, pv.data(), pv.size(), cudaMemcpyHostToDevice));
+    CKB(cudaMemcpy(T->d_pool_mask, pm.data(), pm.size(), cudaMemcpyHostToDevice));
+    if (K)
+    {
+        CKB(cudaMemcpy(T->d_pat_off, off.data(), K * 4, cudaMemcpyHostToDevice));
+        CKB(cudaMemcpy(T->d_pat_len, len.data(), K * 4, cudaMemcpyHostToDevice));
+    }
+    char name[96];
+    snprintf(name, sizeof name, "window%u/stride%u bitmap2^%u%s", w, s, B, plan->case_sensitive ? "" : " fold");
+    plan->filter_name = name;
+    return 0;
+}
+
+void ac_free_tables(Plan *plan)
+{
+    AcDevTables *T = plan->ac;
+    if (!T) return;
+    cudaFree(T->d_bitmap);
+    cudaFree(T->d_slots);
+    cudaFree(T->d_list);
+    cudaFree(T->d_pool_val);
+    cudaFree(T->d_pool_mask);
+    cudaFree(T->d_pat_off);
+    cudaFree(T->d_pat_len);
+    delete T;
+    plan->ac = nullptr;
+}
+
+void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
+{
+    const AcDevTables *T = plan->ac;
+    AcDev A;
+    memset(&A, 0, sizeof A);
+    A.bitmap = T->d_bitmap;
+    A.slots = T->d_slots;
+    A.list = T->d_list;
+    A.pool_val = T->d_pool_val;
+    A.pool_mask = T->d_pool_mask;
+    A.pat_off = T->d_pat_off;
+    A.pat_len = T->d_pat_len;
+    A.B = T->B;
+    A.nslots = T->nslots;
+    A.w = T->w;
+    A.npat = T->npat;
+    A.wmask_lo = (uint32_t)T->wmask;
+    A.wmask_hi = (uint32_t)(T->wmask >> 32);
+    A.fold = T->fold;
+    A.text = a.text;
+    A.avail_len = a.avail_len;
+    A.own_begin = a.own_begin;
+    A.own_end = a.own_end;
+    A.global_offset = a.global_offset;
+    A.prev_byte = a.prev_byte;
+    A.next_byte = a.next_byte;
+    A.out = a.out;
+    A.cap = a.cap;
+    A.counter = a.counter;
+    A.whole_word = a.whole_word;
+    A.want_positions = a.want_positions;
+    // vector groups need the 16-byte vector plus 8 following bytes in bounds
+    const uint64_t total_groups = a.avail_len >= 24 ? (a.avail_len - 24) / 16 + 1 : 0;
+    A.tail_a = total_groups * 16;
+    A.group_begin = a.own_begin / 16;
+    A.group_end = (a.own_end + 3) / 16 + 1; // sampled window of an owned start lies < own_end + s
+    if (A.group_end > total_groups) A.group_end = total_groups;
+    if (A.group_begin > A.group_end) A.group_begin = A.group_end;
+
+    static int sm_count = 0;
+    if (!sm_count)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(k_ac_scan<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    }
+    const size_t smem = (size_t)4 << (T->B - 5);
+    const uint64_t groups = A.group_end - A.group_begin;
+    uint64_t blocks = (groups + 511) / 512;
+    if (blocks == 0) blocks = 1;
+    const uint64_t resident = (uint64_t)sm_count * (smem <= 56 * 1024 ? 4 : (smem <= 112 * 1024 ? 2 : 1));
+    if (blocks > resident) blocks = resident;
+    if (T->s == 1)
+        k_ac_scan<1><<<(unsigned)blocks, 512, smem, st>>>(A);
+    else if (T->s == 2)
+        k_ac_scan<2><<<(unsigned)blocks, 512, smem, st>>>(A);
+    else
+        k_ac_scan<4><<<(unsigned)blocks, 512, smem, st>>>(A);
+    count_launch();
+}
+
+} // namespace kb

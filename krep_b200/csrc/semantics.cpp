@@ -1,0 +1,346 @@
+// semantics.cpp — replays each reference kernel's control flow over the sorted occurrence list that the
+// device produced.  The device enumerates WHERE the literal(s) occur (the byte-scanning work, ~100 % of
+// the reference's run time); which occurrences a given reference kernel counts/reports — its overlap
+// policy, what its cursor does after a -w reject, -c line skipping, the -m limit and its per-kernel
+// quirks — is a walk over that list, O(occurrences), never over the text.  Line boundaries for -c are
+// looked up in the caller's host buffer around occurrences only (memrchr/memchr, as the reference
+// does in find_line_start/find_line_end, krep.c:363-408).
+#define _GNU_SOURCE
+#include <cstdlib>
+#include <cstring>
+#include "common.h"
+
+namespace kb {
+
+// krep.c:175-241 (growth policy: 16, then doubling; memory stays free()-able)
+bool result_push(match_result_t *r, size_t s, size_t e)
+{
+    if (!r) return false;
+    if (r->count >= r->capacity)
+    {
+        uint64_t nc = r->capacity ? r->capacity * 2 : 16;
+        match_position_t *np = r->capacity ? (match_position_t *)realloc(r->positions, nc * sizeof *np)
+                                           : (match_position_t *)malloc(nc * sizeof *np);
+        if (!np)
+        {
+            perror("Error reallocating match positions array");
+            return false;
+        }
+        r->positions = np;
+        r->capacity = nc;
+    }
+    r->positions[r->count].start_offset = s;
+    r->positions[r->count].end_offset = e;
+    r->count++;
+    return true;
+}
+
+static inline size_t line_start(const char *t, size_t n, size_t pos) // krep.c:363
+{
+    if (pos > n) pos = n;
+    if (pos == 0) return 0;
+    const void *nl = memrchr(t, '\n', pos);
+    return nl ? (size_t)((const char *)nl - t) + 1 : 0;
+}
+static inline size_t line_end(const char *t, size_t n, size_t pos) // krep.c:401
+{
+    if (pos >= n) return n;
+    const void *nl = memchr(t + pos, '\n', n - pos);
+    return nl ? (size_t)((const char *)nl - t) : n;
+}
+
+namespace {
+struct Cursor
+{
+    const uint64_t *k;
+    size_t n, i = 0;
+    uint64_t base;
+    size_t pos(size_t j) const { return (size_t)((k[j] >> LIT_TAG_BITS) - base); }
+    bool full(size_t j) const { return (k[j] >> 1) & 1; }
+    bool ww(size_t j) const { return k[j] & 1; }
+    // index of the first full occurrence starting at or after `from`, or n
+    size_t next_full(size_t from)
+    {
+        while (i < n && (pos(i) < from || !full(i))) i++;
+        return i;
+    }
+    // index of the first key (full or prefix-only) at or after `from`, or n
+    size_t next_any(size_t from)
+    {
+        while (i < n && pos(i) < from) i++;
+        return i;
+    }
+};
+} // namespace
+
+// boyer_moore_search, krep.c:1260-1385
+static uint64_t replay_bmh(const search_params_t *P, bool only_matching, size_t m, Cursor c, const char *t, size_t n,
+                           match_result_t *res)
+{
+    if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
+    uint64_t cnt = 0;
+    size_t last_line = SIZE_MAX, from = 0;
+    for (;;)
+    {
+        const size_t j = c.next_full(from);
+        if (j == c.n) break;
+        const size_t s = c.pos(j);
+        if (P->whole_word && !c.ww(j)) { from = s + 1; continue; }
+        bool bumped = false;
+        if (P->count_lines_mode)
+        {
+            const size_t ls = line_start(t, n, s);
+            if (ls != last_line)
+            {
+                cnt++; last_line = ls; bumped = true;
+                if (cnt >= P->max_count) break;
+                const size_t le = line_end(t, n, ls);
+                const size_t nx = le < n ? le + 1 : n;
+                if (nx > s) { from = nx; continue; }
+            }
+        }
+        else
+        {
+            cnt++; bumped = true;
+            if (P->track_positions && res && cnt <= P->max_count) result_push(res, s, s + m);
+        }
+        if (bumped && cnt >= P->max_count) break;
+        from = (only_matching && !P->count_lines_mode) ? s + m : s + 1;
+    }
+    return cnt;
+}
+
+// kmp_search, krep.c:1628-1767
+static uint64_t replay_kmp(const search_params_t *P, size_t m, Cursor c, const char *t, size_t n, match_result_t *res)
+{
+    if (P->max_count == 0) return 0;
+    uint64_t cnt = 0;
+    size_t last_line = SIZE_MAX, from = 0;
+    for (;;)
+    {
+        const size_t j = c.next_full(from);
+        if (j == c.n) break;
+        const size_t s = c.pos(j);
+        from = s + m;
+        if (P->whole_word && !c.ww(j)) continue;
+        if (P->count_lines_mode)
+        {
+            const size_t ls = line_start(t, n, s);
+            if (ls != last_line)
+            {
+                if (P->max_count != SIZE_MAX && cnt >= P->max_count) break;
+                cnt++; last_line = ls;
+                const size_t le = line_end(t, n, ls);
+                from = le < n ? le + 1 : n;
+            }
+        }
+        else
+        {
+            if (P->max_count != SIZE_MAX && cnt >= P->max_count)
+            {
+                if (P->track_positions && res) result_push(res, s, s + m); // krep.c:1719: one past the limit
+                break;
+            }
+            cnt++;
+            if (P->track_positions && res) result_push(res, s, s + m);
+        }
+    }
+    return cnt;
+}
+
+// memchr_search, krep.c:3891-4041 (incl. the 4096-entry staging buffer and its clipped final flush)
+static uint64_t replay_memchr(const search_params_t *P, Cursor c, const char *t, size_t n, match_result_t *res)
+{
+    if (P->max_count == 0) return 0;
+    enum { BUF = 4096 };
+    match_position_t *buf = (match_position_t *)malloc(BUF * sizeof *buf);
+    size_t nb = 0;
+    uint64_t cnt = 0;
+    size_t last_line = SIZE_MAX, from = 0;
+    const bool tracking = P->track_positions && res;
+    while (from < n)
+    {
+        const size_t j = c.next_full(from);
+        if (j == c.n) break;
+        const size_t s = c.pos(j);
+        if (P->whole_word && !c.ww(j)) { from = s + 1; continue; }
+        if (P->count_lines_mode)
+        {
+            const size_t ls = line_start(t, n, s);
+            if (ls != last_line)
+            {
+                if (P->max_count != SIZE_MAX && cnt >= P->max_count) break;
+                cnt++; last_line = ls;
+                const size_t le = line_end(t, n, ls);
+                from = le < n ? le + 1 : n;
+            }
+            else from = s + 1;
+        }
+        else
+        {
+            if (P->max_count != SIZE_MAX && cnt >= P->max_count)
+            {
+                if (tracking)
+                {
+                    if (nb < BUF) { buf[nb].start_offset = s; buf[nb].end_offset = s + 1; nb++; }
+                    else result_push(res, s, s + 1);
+                }
+                break;
+            }
+            cnt++;
+            if (tracking)
+            {
+                if (nb >= BUF)
+                {
+                    for (size_t q = 0; q < nb; q++) result_push(res, buf[q].start_offset, buf[q].end_offset);
+                    nb = 0;
+                }
+                buf[nb].start_offset = s; buf[nb].end_offset = s + 1; nb++;
+            }
+            from = s + 1;
+        }
+    }
+    if (tracking && nb > 0)
+    {
+        const uint64_t have = res->count;
+        const uint64_t room = (P->max_count == SIZE_MAX) ? nb : (have >= P->max_count ? 0 : P->max_count - have);
+        const size_t lim = nb < room ? nb : (size_t)room;
+        for (size_t q = 0; q < lim; q++) result_push(res, buf[q].start_offset, buf[q].end_offset);
+    }
+    free(buf);
+    return cnt;
+}
+
+// memchr_short_search, krep.c:4371-4503.  With -o the list holds every first-byte hit (full bit set on
+// real occurrences) because the reference's cursor jumps pattern_len past ANY first-byte hit.
+static uint64_t replay_memchr_short(const search_params_t *P, bool only_matching, size_t m, Cursor c, const char *t,
+                                    size_t n, match_result_t *res)
+{
+    if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
+    if (m < 2 || m > 3 || n < m) return 0;
+    uint64_t cnt = 0;
+    size_t last_line = SIZE_MAX, cur = 0;
+    while (n - cur >= m)
+    {
+        const size_t j = only_matching ? c.next_any(cur) : c.next_full(cur);
+        if (j == c.n) break;
+        const size_t h = c.pos(j);
+        if (h > n - m) break; // memchr range is remaining_len - pattern_len + 1 (krep.c:4401)
+        if (c.full(j))
+        {
+            if (P->whole_word && !c.ww(j)) { cur = h + 1; continue; }
+            bool bumped = false;
+            if (P->count_lines_mode)
+            {
+                const size_t ls = line_start(t, n, h);
+                if (ls != last_line)
+                {
+                    cnt++; last_line = ls; bumped = true;
+                    if (cnt >= P->max_count) break;
+                    const size_t le = line_end(t, n, ls);
+                    const size_t nx = le < n ? le + 1 : n;
+                    if (nx > cur) { cur = nx; continue; }
+                }
+            }
+            else
+            {
+                cnt++; bumped = true;
+                if (P->track_positions && res && cnt <= P->max_count) result_push(res, h, h + m);
+            }
+            if (bumped && cnt >= P->max_count) break;
+        }
+        const size_t adv = (h - cur) + (only_matching ? m : 1);
+        if (adv > n - cur) break;
+        cur += adv;
+    }
+    return cnt;
+}
+
+// simd_sse42_search, krep.c:4702-4869 (preconditions already resolved by the caller)
+static uint64_t replay_sse42(const search_params_t *P, bool only_matching, size_t m, Cursor c, const char *t, size_t n,
+                             match_result_t *res)
+{
+    if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
+    uint64_t cnt = 0;
+    size_t last_line = SIZE_MAX, cur = 0;
+    while (n - cur >= m)
+    {
+        const size_t j = c.next_full(cur);
+        if (j == c.n) break;
+        const size_t s = c.pos(j);
+        if (!P->whole_word || c.ww(j))
+        {
+            bool bumped = false;
+            if (P->count_lines_mode)
+            {
+                const size_t ls = line_start(t, n, s);
+                if (ls != last_line)
+                {
+                    if (cnt >= P->max_count) break;
+                    cnt++; last_line = ls; bumped = true;
+                    const size_t le = line_end(t, n, ls);
+                    if (le < n) { cur = le + 1; continue; }
+                }
+            }
+            else
+            {
+                if (cnt >= P->max_count) break;
+                cnt++; bumped = true;
+                if (P->track_positions && res && cnt <= P->max_count) result_push(res, s, s + m);
+            }
+            if (bumped && cnt >= P->max_count) break;
+        }
+        cur = only_matching ? s + 1 : s + m;
+        if (cur > n) cur = n;
+    }
+    return cnt;
+}
+
+uint64_t replay_literal(int algo, const search_params_t *P, bool only_matching, uint32_t m, const Replay &r,
+                        match_result_t *res)
+{
+    Cursor c{r.keys, r.n, 0, r.base};
+    switch (algo)
+    {
+    case KREP_B200_ALGO_KMP: return replay_kmp(P, m, c, r.text, r.text_len, res);
+    case KREP_B200_ALGO_MEMCHR: return replay_memchr(P, c, r.text, r.text_len, res);
+    case KREP_B200_ALGO_MEMCHR_SHORT: return replay_memchr_short(P, only_matching, m, c, r.text, r.text_len, res);
+    case KREP_B200_ALGO_SSE42: return replay_sse42(P, only_matching, m, c, r.text, r.text_len, res);
+    default: return replay_bmh(P, only_matching, m, c, r.text, r.text_len, res);
+    }
+}
+
+// aho_corasick_search, aho_corasick.c:299-466; keys arrive in emission order, -w rejects already dropped
+uint64_t replay_ac(const search_params_t *P, const Replay &r, match_result_t *res)
+{
+    if (P->max_count == 0) return 0;
+    const size_t maxc = P->max_count;
+    uint64_t found = 0;
+    size_t last_line = SIZE_MAX;
+    for (size_t j = 0; j < r.n; j++)
+    {
+        if (found >= maxc) return found;
+        const uint64_t key = r.keys[j];
+        const size_t e = (size_t)((key >> AC_END_SHIFT) - r.base);
+        const size_t len = 1024 - (size_t)((key >> AC_LEN_SHIFT) & 1023);
+        const size_t s = e - len;
+        if (P->count_lines_mode)
+        {
+            const size_t ls = line_start(r.text, r.text_len, s);
+            if (ls != last_line)
+            {
+                found++; last_line = ls;
+                if (found >= maxc) return found;
+            }
+        }
+        else
+        {
+            found++;
+            if (P->track_positions && res) result_push(res, s, e);
+            if (found >= maxc) return found;
+        }
+    }
+    return found;
+}
+
+} // namespace kb

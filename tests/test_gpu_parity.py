@@ -1,0 +1,125 @@
+"""-m gpu: parity of the CUDA path, called through the C ABI, against the oracle.
+Bit-exact bar: count, every (start,end) and their order."""
+import ctypes as C
+import json
+import os
+import random
+
+import pytest
+
+import oracle_util as ou
+from krep_b200 import lib
+from krep_b200.abi import (ALGO_AC, ALGO_BMH, ALGO_SSE42, CORPUS_EMBED_HALF, CORPUS_RANDOM_CASE, Params, SIZE_MAX)
+from test_oracle import _vectors, params_from, random_case, text_from
+
+pytestmark = pytest.mark.gpu
+
+
+def checker():
+    return ou.reference() or ou.port()
+
+
+@pytest.mark.parametrize("v", _vectors(), ids=lambda v: f'{v["func"]}:{v["pat"][0][:8]}:{v["src"].split()[0]}')
+def test_reference_test_vectors_through_c_abi(v):
+    cnt, pos = lib.search(v["func"], params_from(v), text_from(v), with_result=v.get("res", False))
+    assert cnt == v["expect"], v["src"]
+    if "npos" in v:
+        assert len(pos) == v["npos"], v["src"]
+
+
+def test_committed_reference_fixtures_through_c_abi():
+    with open(os.path.join(os.path.dirname(__file__), "golden", "ref_fixtures.json")) as f:
+        fx = json.load(f)["cases"]
+    for c in fx:
+        p = Params([bytes.fromhex(x) for x in c["pat"]], case_sensitive=c["cs"], count=c["count"],
+                   only_matching=c["o"], whole_word=c["w"], max_count=c["m"] if c["m"] >= 0 else SIZE_MAX)
+        cnt, pos = lib.search(c["func"], p, bytes.fromhex(c["text"]), with_result=c["res"])
+        assert cnt == c["count_out"] and [list(x) for x in pos] == c["pos_out"], c
+
+
+@pytest.mark.parametrize("func", list(ou.FUNCS))
+def test_random_differential_vs_oracle(func):
+    rng = random.Random(4242 + len(func))
+    chk = checker()
+    for _ in range(700):
+        pats, text, opts, with_res = random_case(rng, func)
+        got = lib.search(func, Params(pats, **opts), text, with_result=with_res)
+        want = chk.run(func, Params(pats, **opts), text, with_result=with_res)
+        assert got == want, (func, pats, text, opts, with_res, got, want)
+
+
+def _mixed_text(rng, n):
+    words = [b"the", b"quick", b"Brown", b"fox_1", b"needle", b"NEEDLE", b"ab", b"abab", b"aaa", b"x"]
+    out = bytearray()
+    while len(out) < n:
+        out += rng.choice(words)
+        out += rng.choice([b" ", b" ", b"\n", b"", b",", b"_"])
+    return bytes(out[:n])
+
+
+@pytest.mark.parametrize("func,pat", [
+    ("sse42", b"needle"), ("sse42", b"the quick"), ("sse42", b"abab"), ("boyer_moore", b"aaa"),
+    ("boyer_moore", b"needle Brown"), ("kmp", b"abab"), ("memchr", b"x"), ("memchr_short", b"ab"),
+    ("boyer_moore", b"the quick Brown fox_1 needle NEEDLE"), ("sse42", b"fox_1 needle NEE"),
+])
+@pytest.mark.parametrize("opts", [
+    dict(), dict(case_sensitive=False), dict(whole_word=True), dict(count=True), dict(only_matching=True),
+    dict(count=True, only_matching=True), dict(max_count=5), dict(whole_word=True, only_matching=True, case_sensitive=False),
+    dict(count=True, whole_word=True, max_count=3),
+])
+def test_medium_text_all_modes(func, pat, opts):
+    rng = random.Random(9)
+    text = _mixed_text(rng, 300_000)
+    got = lib.search(func, Params(pat, **opts), text)
+    want = checker().run(func, Params(pat, **opts), text)
+    assert got == want
+
+
+def test_chunked_staging_path_matches_single_copy(monkeypatch):
+    """Host text larger than the staging chunk: occurrences straddling chunk edges, -w context across edges."""
+    rng = random.Random(5)
+    text = bytearray(_mixed_text(rng, 5 * (1 << 20) + 12345))
+    pat = b"straddle_me"
+    mb = 1 << 20
+    for c in range(1, 5):
+        for delta in (-len(pat), -5, -1, 0, 1):
+            s = c * mb + delta
+            text[s:s + len(pat)] = pat
+    text[2 * mb - 6 - 1] = ord("Z")          # word char right before an occurrence that ends at the edge region
+    text = bytes(text)
+    monkeypatch.setenv("KREP_B200_STAGE_MB", "1")
+    monkeypatch.setenv("KREP_B200_CHUNK_MB", "1")
+    for func, opts in [("sse42", {}), ("boyer_moore", dict(whole_word=True)), ("boyer_moore", dict(count=True)),
+                       ("kmp", dict(case_sensitive=False)), ("sse42", dict(count=True, only_matching=True))]:
+        got = lib.search(func, Params(pat, **opts), text)
+        want = checker().run(func, Params(pat, **opts), text)
+        assert got == want, (func, opts)
+    pats = [b"straddle_me", b"addle", b"fox_1 ne", b"quick"]
+    got = lib.search("aho_corasick", Params(pats), text)
+    want = checker().run("aho_corasick", Params(pats), text)
+    assert got == want
+
+
+def test_aho_corasick_many_patterns():
+    rng = random.Random(11)
+    text = _mixed_text(rng, 400_000)
+    alpha = b"abcdefghijklmnopqrstuvwxyz"
+    pats = [bytes(rng.choice(alpha) for _ in range(rng.randint(6, 12))) for _ in range(990)]
+    pats += [b"needle", b"quick Brow", b"fox_1 needle", b"NEEDLE", b"the quick", b"abababab", b"aaaaaa", b"needle",
+             b"ox_1 nee", b"Brown fox_1"]
+    for opts in [dict(), dict(case_sensitive=False), dict(whole_word=True), dict(count=True), dict(max_count=17)]:
+        got = lib.search("aho_corasick", Params(pats, **opts), text)
+        want = checker().run("aho_corasick", Params(pats, **opts), text)
+        assert got == want, opts
+        assert got[0] > 0
+
+
+def test_aho_corasick_short_and_mixed_lengths():
+    rng = random.Random(12)
+    text = _mixed_text(rng, 100_000)
+    for pats in ([b"a", b"ab", b"the quick"], [b"x", b"ee"], [b"ab", b"abab", b"ababab"], [b"needle", b"ne", b"e"],
+                 [b"quick", b"uick ", b"fox_1"], [b"", b"the"]):
+        for opts in [dict(), dict(case_sensitive=False), dict(whole_word=True)]:
+            got = lib.search("aho_corasick", Params(pats, **opts), text)
+            want = checker().run("aho_corasick", Params(pats, **opts), text)
+            assert got == want, (pats, opts)

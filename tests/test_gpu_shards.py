@@ -1,0 +1,117 @@
+"""-m gpu: HBM-resident shard API — device corpus == host twin, shard ownership/halo, size-independent
+properties at larger sizes."""
+import ctypes as C
+
+import pytest
+import torch
+
+import gpu_util as gu
+import oracle_util as ou
+from krep_b200 import lib
+from krep_b200.abi import (ALGO_AC, ALGO_BMH, ALGO_SSE42, CORPUS_EMBED_HALF, CORPUS_RANDOM_CASE, Params)
+
+pytestmark = pytest.mark.gpu
+NEEDLE = b"qzXv9Kpw"
+
+
+def checker():
+    return ou.reference() or ou.port()
+
+
+def test_device_corpus_equals_host_twin():
+    for flags, needle in [(0, NEEDLE), (CORPUS_RANDOM_CASE, b"QzXv"), (CORPUS_EMBED_HALF, b"needleneedle0016")]:
+        spec = lib.make_spec(0x5EED0001, 0x5EED0002, 4096, needle, flags)
+        for off, n in [(0, 100_000), (4096 * 7 + 16, 33_333), (1 << 33, 70_001)]:
+            dev = gu.device_corpus(spec, off, n)
+            assert bytes(dev[:n].cpu().numpy()) == lib.corpus_host(spec, off, n)
+
+
+@pytest.mark.parametrize("pat,algo,func,opts,flags", [
+    (NEEDLE, ALGO_SSE42, "sse42", {}, 0),
+    (b"QzXv", ALGO_BMH, "boyer_moore", dict(case_sensitive=False), CORPUS_RANDOM_CASE),
+    (b"needleneedle0016", ALGO_SSE42, "sse42", dict(whole_word=True), CORPUS_EMBED_HALF),
+    (b"the", ALGO_BMH, "boyer_moore", {}, 0),
+])
+def test_whole_shard_matches_oracle_on_corpus(pat, algo, func, opts, flags):
+    L = lib.load()
+    n = 32 * (1 << 20) + 77
+    spec = lib.make_spec(7, 8, 1 << 16, pat if len(pat) > 3 else NEEDLE, flags)
+    dev = gu.device_corpus(spec, 0, n)
+    host = bytes(dev[:n].cpu().numpy())
+    p = Params(pat, **opts)
+    plan = L.krep_b200_plan_create(p.ref(), algo)
+    lib.check(L)
+    try:
+        out = gu.scan(plan, dev, n)
+        got = gu.collect(plan, p, out)
+        want = checker().run(func, Params(pat, **opts), host)
+        assert got == want
+        assert got[0] >= n // (1 << 16) // 2 - 2
+        # count-only launch gives the same count
+        out2 = gu.scan(plan, dev, n, want_positions=False)
+        assert out2.count == out.count
+    finally:
+        L.krep_b200_plan_destroy(plan)
+
+
+def test_shards_with_halo_union_equals_whole():
+    """each shard owns matches by start offset, reads a halo, and takes -w context from its neighbours."""
+    L = lib.load()
+    n = 8 * (1 << 20) + 1234
+    pat = b"needleneedle0016"
+    spec = lib.make_spec(21, 22, 1 << 14, pat, CORPUS_EMBED_HALF)
+    whole = gu.device_corpus(spec, 0, n)
+    host = bytes(whole[:n].cpu().numpy())
+    for opts, algo in [(dict(whole_word=True), ALGO_SSE42), (dict(), ALGO_BMH)]:
+        p = Params(pat, **opts)
+        plan = L.krep_b200_plan_create(p.ref(), algo)
+        try:
+            ref = gu.collect(plan, p, gu.scan(plan, whole, n))
+            for nshards in (2, 3, 8):
+                S = ((n + nshards - 1) // nshards + 15) // 16 * 16
+                merged = []
+                total = 0
+                for g in range(nshards):
+                    b, e = g * S, min((g + 1) * S, n)
+                    avail = min(e + len(pat), n)          # halo: pattern_len bytes (occurrence + following byte)
+                    shard = gu.device_corpus(spec, b, avail - b)
+                    out = gu.scan(plan, shard, avail - b, own_begin=0, own_end=e - b, global_offset=b,
+                                  prev_byte=host[b - 1] if b else -1, next_byte=host[avail] if avail < n else -1)
+                    cnt, pos = gu.collect(plan, p, out)
+                    total += cnt
+                    merged += pos
+                assert (total, merged) == ref, (opts, nshards)
+        finally:
+            L.krep_b200_plan_destroy(plan)
+
+
+def test_properties_at_1gib():
+    """Size-independent checks at a size the oracle would not finish quickly: sortedness, every reported
+    offset really holds the needle, every intact plant is reported, count-only == list length,
+    and the shard decomposition agrees with the single-shard result."""
+    L = lib.load()
+    n = 1 << 30
+    period = 1 << 20
+    spec = lib.make_spec(0x5EED0001, 0x5EED0002, period, NEEDLE)
+    dev = gu.device_corpus(spec, 0, n)
+    p = Params(NEEDLE)
+    plan = L.krep_b200_plan_create(p.ref(), ALGO_SSE42)
+    try:
+        out = gu.scan(plan, dev, n)
+        cnt, pos = gu.collect(plan, p, out)
+        assert cnt == len(pos) >= n // period - 8
+        starts = torch.tensor([s for s, _ in pos], dtype=torch.int64, device="cuda")
+        assert bool((starts[1:] > starts[:-1]).all())
+        idx = starts[:, None] + torch.arange(len(NEEDLE), device="cuda")[None, :]
+        needle_t = torch.tensor(list(NEEDLE), dtype=torch.uint8, device="cuda")
+        assert bool((dev[idx] == needle_t[None, :]).all())
+        assert gu.scan(plan, dev, n, want_positions=False).count == cnt
+        # two shards
+        half = n // 2
+        a = gu.scan(plan, dev, half + 16, own_begin=0, own_end=half, next_byte=-1)
+        ca, pa = gu.collect(plan, p, a)
+        b = gu.scan(plan, dev, n, own_begin=half, own_end=n)
+        cb, pb = gu.collect(plan, p, b)
+        assert pa + pb == pos and ca + cb == cnt
+    finally:
+        L.krep_b200_plan_destroy(plan)
