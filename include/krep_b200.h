@@ -200,6 +200,10 @@ typedef struct
 int krep_b200_scan_shard(const krep_b200_plan_t *plan, const krep_b200_shard_t *shard,
                          int want_positions, void *stream, krep_b200_device_result_t *out);
 
+/* Copy the first min(out->stored, max_keys) sorted keys of a shard result into another device
+ * buffer (device-to-device, on `stream`), e.g. a torch tensor that is then gathered with NCCL. */
+int krep_b200_export_keys(const krep_b200_device_result_t *dev, void *d_dst, uint64_t max_keys, void *stream);
+
 /* Timing hook for bench.py: device time in milliseconds of the scan kernel(s)
  * of the most recent krep_b200_scan_shard / search call on this thread,
  * measured with CUDA events on the launching stream (kernel only, no sort). */

@@ -543,6 +543,19 @@ int krep_b200_scan_shard(const krep_b200_plan_t *plan, const krep_b200_shard_t *
     return rc;
 }
 
+int krep_b200_export_keys(const krep_b200_device_result_t *dev, void *d_dst, uint64_t max_keys, void *stream)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    clear_error();
+    if (!dev || !d_dst) return -3;
+    const uint64_t n = dev->stored < max_keys ? dev->stored : max_keys;
+    if (n == 0) return 0;
+    cudaStream_t s = stream ? (cudaStream_t)stream : engine().scan_stream;
+    CK(cudaMemcpyAsync(d_dst, dev->d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    if (!stream) CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
 uint64_t krep_b200_ac_key_end(uint64_t key) { return key >> AC_END_SHIFT; }
 uint64_t krep_b200_ac_key_start(uint64_t key)
 {

@@ -76,6 +76,8 @@ def load():
     L.krep_b200_replay.argtypes = [C.c_int, C.POINTER(SearchParams), C.c_bool, C.POINTER(C.c_uint64), C.c_uint64,
                                    C.c_void_p, C.c_size_t, C.POINTER(MatchResult)]
     L.krep_b200_replay.restype = C.c_uint64
+    L.krep_b200_export_keys.argtypes = [C.POINTER(DeviceResult), C.c_void_p, C.c_uint64, C.c_void_p]
+    L.krep_b200_export_keys.restype = C.c_int
     L.krep_b200_last_kernel_ms.restype = C.c_float
     L.krep_b200_launch_count.restype = C.c_uint64
     for n in ("krep_b200_ac_key_end", "krep_b200_ac_key_start"):
