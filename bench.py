@@ -59,56 +59,75 @@ def multi_patterns(n, needle):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md).  The sampler runs from before the warm-up
+    (nvidia-smi takes ~100 ms to produce its first line) and only samples whose timestamp falls inside the
+    timed region are reported; if the region was too short to contain one, the nearest samples are used."""
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+            q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
                  "clocks_event_reasons.sw_power_cap")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if not self.proc:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 7:
+                if len(f) < 8:
                     continue
                 try:
-                    sm.append(float(f[0]))
-                    mx.append(float(f[1]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), float(f[3]), f[4:8]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
-        return out
+        if not rows:
+            return out
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        used = inside
+        if not used:  # region shorter than the sampling period: take the samples closest to it
+            mid = 0.5 * ((self.t0 or rows[-1][0]) + (self.t1 or rows[-1][0]))
+            used = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+        reasons = set()
+        for r in used:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(r[1] for r in used), "sm_max_mhz": max(r[2] for r in used),
+                "power_w_max": max(r[3] for r in used), "reasons": sorted(reasons), "samples": len(used),
+                "samples_inside_timed_region": len(inside)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -215,7 +234,7 @@ def run_cpu_reference(wl_name, wl, sample_bytes, steps, warmup, keep_file=False)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gib", type=float, default=10.0, help="corpus GiB per GPU")
@@ -320,13 +339,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3) if args.steps else 0):
         step()
     L.krep_b200_reset_launch_count()
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
     e0.record(stream)
@@ -336,6 +356,7 @@ def main():
         kernel_ms.append(kms)
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = e0.elapsed_time(e1)
     launches = int(L.krep_b200_launch_count())

@@ -44,6 +44,7 @@ struct AcDevTables
     uint32_t B = 0, nslots = 0, w = 0, s = 0, npat = 0;
     uint64_t wmask = 0; // low w bytes
     uint32_t fold = 0xFFFFFFFFu;
+    uint32_t mul_lo = 0, mul_hi = 0, bit_shift = 0;
 };
 
 struct AcDev
@@ -55,6 +56,7 @@ struct AcDev
     const uint32_t *pat_off, *pat_len;
     uint32_t B, nslots, w, npat;
     uint32_t wmask_lo, wmask_hi, fold;
+    uint32_t mul_lo, mul_hi, bit_shift; // hash multipliers (low zero bytes mask the window), bit-index shift for w < 4
     // launch
     const uint8_t *text;
     uint64_t avail_len, own_begin, own_end, global_offset;
@@ -68,7 +70,6 @@ struct AcDev
 
 static constexpr uint32_t HC1 = 0x9E3779B1u, HC2 = 0x85EBCA77u;
 
-__host__ __device__ __forceinline__ uint32_t win_hash(uint32_t lo, uint32_t hi) { return lo * HC1 + hi * HC2; }
 __host__ __device__ __forceinline__ uint32_t slot_hash(uint32_t lo, uint32_t hi)
 {
     uint32_t h = (lo ^ (hi * 0xC2B2AE3Du)) * 0x27D4EB2Fu;
@@ -108,8 +109,8 @@ __device__ __noinline__ unsigned ac_verify_emit(const AcDev &A, uint32_t k, long
     return 1;
 }
 
-// window value (lo,hi already folded+masked) at sampled position a passed the bitmap
-__device__ __noinline__ unsigned ac_slow(const AcDev &A, uint64_t a, uint32_t lo, uint32_t hi)
+// window value (lo,hi canonical: folded + masked to w bytes) at sampled position a passed the bitmap
+__device__ __forceinline__ unsigned ac_probe(const AcDev &A, uint64_t a, uint32_t lo, uint32_t hi)
 {
     const uint64_t key = ((uint64_t)hi << 32) | lo;
     uint32_t h = slot_hash(lo, hi) & (A.nslots - 1);
@@ -131,8 +132,63 @@ __device__ __noinline__ unsigned ac_slow(const AcDev &A, uint64_t a, uint32_t lo
     }
 }
 
+// Rare path: `hits` has one bit per bitmap lookup of the 16-byte group g (first lookup = highest bit).
+// Re-reads the window bytes (L1/L2 hits), rebuilds the canonical window value and probes the exact table.
 template <int S>
-__global__ void __launch_bounds__(512, 1) k_ac_scan(const __grid_constant__ AcDev A)
+__device__ __noinline__ unsigned ac_detour(const AcDev &A, uint64_t g, uint32_t hits)
+{
+    constexpr int NLOOK = 16 / S;
+    unsigned n = 0;
+    while (hits)
+    {
+        const int bit = 31 - __clz(hits);
+        hits &= ~(1u << bit);
+        const uint64_t a = g * 16 + (uint64_t)(NLOOK - 1 - bit) * S;
+        const uint8_t *t = A.text + a;
+        uint32_t lo = 0, hi = 0;
+        for (uint32_t i = 0; i < A.w; i++)
+        {
+            if (i < 4) lo |= (uint32_t)t[i] << (8 * i);
+            else hi |= (uint32_t)t[i] << (8 * (i - 4));
+        }
+        n += ac_probe(A, a, lo & A.fold, hi & A.fold);
+    }
+    return n;
+}
+
+// One 16-byte group: 16/S bitmap lookups.  Per lookup: window extraction (free for word-aligned windows,
+// two PRMT/SHF otherwise), hash = lo*M1 + hi*M2 on the FMA pipe (the multipliers' low zero bytes mask the
+// window to w bytes for free), bitmap byte address = mulhi(hash, bitmap_bytes) & ~3 (well-mixed high hash
+// bits), bit index = low hash bits (shifted for w < 4), one LDS.
+template <int S, bool FOLD>
+__device__ __forceinline__ uint32_t ac_group_hits(const uint32_t *s_bitmap, uint4 v, uint2 nx, uint32_t fold, uint32_t m1,
+                                                  uint32_t m2, uint32_t nbytes, uint32_t bit_shift)
+{
+    uint32_t w[6] = {v.x, v.y, v.z, v.w, nx.x, nx.y};
+    if (FOLD)
+    {
+#pragma unroll
+        for (int i = 0; i < 6; i++) w[i] &= fold;
+    }
+    uint32_t hits = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int r = 0; r < 4; r += S)
+        {
+            const uint32_t lo = r == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * r);
+            const uint32_t hi = r == 0 ? w[k + 1] : __funnelshift_r(w[k + 1], w[k + 2], 8 * r);
+            const uint32_t h = lo * m1 + hi * m2;
+            const uint32_t addr = __umulhi(h, nbytes) & ~3u;
+            const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_bitmap) + addr);
+            const uint32_t sel = S == 1 ? (h >> bit_shift) : h;
+            hits = hits * 2 + (__funnelshift_r(word, 0, sel) & 1u);
+        }
+    return hits;
+}
+
+template <int S, bool FOLD>
+__global__ void __launch_bounds__(1024, 1) k_ac_scan(const __grid_constant__ AcDev A)
 {
     extern __shared__ uint32_t s_bitmap[];
     {
@@ -143,37 +199,42 @@ __global__ void __launch_bounds__(512, 1) k_ac_scan(const __grid_constant__ AcDe
     }
     __syncthreads();
     const uint4 *__restrict__ t4 = reinterpret_cast<const uint4 *>(A.text);
-    const uint32_t fold = A.fold, mlo = A.wmask_lo & fold, mhi = A.wmask_hi & fold, shift = 32 - A.B;
+    const uint32_t fold = A.fold, m1 = A.mul_lo, m2 = A.mul_hi, nbytes = 1u << (A.B - 3), bit_shift = A.bit_shift;
     unsigned long long local_cnt = 0;
-    for (uint64_t g = A.group_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.group_end;
-         g += (uint64_t)gridDim.x * blockDim.x)
+    constexpr int UNROLL = 2;
+    const uint64_t tile = (uint64_t)blockDim.x * UNROLL;
+    const uint64_t stride = (uint64_t)gridDim.x * tile;
+    uint64_t g0 = A.group_begin + (uint64_t)blockIdx.x * tile;
+    for (; g0 + tile <= A.group_end; g0 += stride)
     {
-        const uint4 v = __ldcs(t4 + g);
-        const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(t4 + g + 1)); // 8 bytes after the vector (in bounds by group_end)
-        const uint32_t w[6] = {v.x, v.y, v.z, v.w, nx.x, nx.y};
-        uint32_t any = 0;
+        uint4 v[UNROLL];
+        uint2 nx[UNROLL];
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-#pragma unroll
-            for (int r = 0; r < 4; r += S)
-            {
-                const uint32_t lo = (r == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * r)) & mlo;
-                const uint32_t hi = (r == 0 ? w[k + 1] : __funnelshift_r(w[k + 1], w[k + 2], 8 * r)) & mhi;
-                const uint32_t idx = win_hash(lo, hi) >> shift;
-                any |= (s_bitmap[idx >> 5] >> (idx & 31)) & 1u;
-            }
-        if (any)
+        for (int u = 0; u < UNROLL; u++)
         {
+            const uint4 *q = t4 + g0 + (uint64_t)u * blockDim.x + threadIdx.x;
+            v[u] = __ldcs(q);
+            nx[u] = __ldg(reinterpret_cast<const uint2 *>(q + 1)); // 8 bytes after the vector (in bounds by group_end)
+        }
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-#pragma unroll
-                for (int r = 0; r < 4; r += S)
-                {
-                    const uint32_t lo = (r == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * r)) & mlo;
-                    const uint32_t hi = (r == 0 ? w[k + 1] : __funnelshift_r(w[k + 1], w[k + 2], 8 * r)) & mhi;
-                    const uint32_t idx = win_hash(lo, hi) >> shift;
-                    if ((s_bitmap[idx >> 5] >> (idx & 31)) & 1u) local_cnt += ac_slow(A, g * 16 + 4 * k + r, lo, hi);
-                }
+        for (int u = 0; u < UNROLL; u++)
+        {
+            const uint32_t hits = ac_group_hits<S, FOLD>(s_bitmap, v[u], nx[u], fold, m1, m2, nbytes, bit_shift);
+            if (hits) local_cnt += ac_detour<S>(A, g0 + (uint64_t)u * blockDim.x + threadIdx.x, hits);
+        }
+    }
+    if (g0 < A.group_end)
+    {
+        for (int u = 0; u < UNROLL; u++)
+        {
+            const uint64_t g = g0 + (uint64_t)u * blockDim.x + threadIdx.x;
+            if (g < A.group_end)
+            {
+                const uint4 v = __ldcs(t4 + g);
+                const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(t4 + g + 1));
+                const uint32_t hits = ac_group_hits<S, FOLD>(s_bitmap, v, nx, fold, m1, m2, nbytes, bit_shift);
+                if (hits) local_cnt += ac_detour<S>(A, g, hits);
+            }
         }
     }
     // tail: occurrences whose sampled window lies beyond the vector loop — brute force, lanes over patterns
@@ -244,6 +305,10 @@ int ac_build_tables(Plan *plan)
     T->s = s;
     T->wmask = w >= 8 ? ~0ull : ((1ull << (8 * w)) - 1);
     T->fold = plan->case_sensitive ? 0xFFFFFFFFu : 0xDFDFDFDFu;
+    // hash = lo*mul_lo + hi*mul_hi; a multiplier with k low zero bytes ignores the top k bytes of its operand
+    T->mul_lo = w >= 4 ? HC1 : (HC1 << (8 * (4 - w)));
+    T->mul_hi = w > 4 ? (w >= 8 ? HC2 : (HC2 << (8 * (8 - w)))) : 0u;
+    T->bit_shift = w >= 4 ? 0u : 8 * (4 - w);
 
     // pattern pool (exact compare data) + window entries
     std::vector<uint32_t> off(K), len(K);
@@ -283,8 +348,9 @@ int ac_build_tables(Plan *plan)
         size_t j = i;
         while (j < ents.size() && ents[j].key == ents[i].key) { list[j] = ents[j].e; j++; }
         const uint32_t lo = (uint32_t)ents[i].key, hi = (uint32_t)(ents[i].key >> 32);
-        const uint32_t idx = win_hash(lo, hi) >> (32 - B);
-        bitmap[idx >> 5] |= 1u << (idx & 31);
+        const uint32_t hsh = lo * T->mul_lo + hi * T->mul_hi;
+        const uint32_t addr = (uint32_t)(((uint64_t)hsh * (1u << (B - 3))) >> 32) & ~3u;
+        bitmap[addr >> 2] |= 1u << ((s == 1 ? (hsh >> T->bit_shift) : hsh) & 31);
         uint32_t h = slot_hash(lo, hi) & (nslots - 1);
         while (slots[h].count) h = (h + 1) & (nslots - 1);
         slots[h] = AcSlot{ents[i].key, (uint32_t)i, (uint32_t)(j - i)};
@@ -349,6 +415,9 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     A.wmask_lo = (uint32_t)T->wmask;
     A.wmask_hi = (uint32_t)(T->wmask >> 32);
     A.fold = T->fold;
+    A.mul_lo = T->mul_lo;
+    A.mul_hi = T->mul_hi;
+    A.bit_shift = T->bit_shift;
     A.text = a.text;
     A.avail_len = a.avail_len;
     A.own_begin = a.own_begin;
@@ -375,22 +444,27 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_ac_scan<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        cudaFuncSetAttribute(k_ac_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        cudaFuncSetAttribute(k_ac_scan<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     }
     const size_t smem = (size_t)4 << (T->B - 5);
     const uint64_t groups = A.group_end - A.group_begin;
-    uint64_t blocks = (groups + 511) / 512;
+    uint64_t blocks = (groups + 2047) / 2048;
     if (blocks == 0) blocks = 1;
-    const uint64_t resident = (uint64_t)sm_count * (smem <= 56 * 1024 ? 4 : (smem <= 112 * 1024 ? 2 : 1));
+    const uint64_t resident = (uint64_t)sm_count * (smem <= 100 * 1024 ? 2 : 1); // 1024-thread CTAs
     if (blocks > resident) blocks = resident;
+    const bool f = T->fold != 0xFFFFFFFFu;
+    const unsigned nb = (unsigned)blocks;
     if (T->s == 1)
-        k_ac_scan<1><<<(unsigned)blocks, 512, smem, st>>>(A);
+        f ? k_ac_scan<1, true><<<nb, 1024, smem, st>>>(A) : k_ac_scan<1, false><<<nb, 1024, smem, st>>>(A);
     else if (T->s == 2)
-        k_ac_scan<2><<<(unsigned)blocks, 512, smem, st>>>(A);
+        f ? k_ac_scan<2, true><<<nb, 1024, smem, st>>>(A) : k_ac_scan<2, false><<<nb, 1024, smem, st>>>(A);
     else
-        k_ac_scan<4><<<(unsigned)blocks, 512, smem, st>>>(A);
+        f ? k_ac_scan<4, true><<<nb, 1024, smem, st>>>(A) : k_ac_scan<4, false><<<nb, 1024, smem, st>>>(A);
     count_launch();
 }
 
