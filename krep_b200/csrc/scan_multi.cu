@@ -132,37 +132,24 @@ __device__ __forceinline__ unsigned ac_probe(const AcDev &A, uint64_t a, uint32_
     }
 }
 
-// Rare path: `hits` has one bit per bitmap lookup of the 16-byte group g (first lookup = highest bit).
-// Re-reads the window bytes (L1/L2 hits), rebuilds the canonical window value and probes the exact table.
-template <int S>
-__device__ __noinline__ unsigned ac_detour(const AcDev &A, uint64_t g, uint32_t hits)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
 {
-    constexpr int NLOOK = 16 / S;
-    unsigned n = 0;
-    while (hits)
-    {
-        const int bit = 31 - __clz(hits);
-        hits &= ~(1u << bit);
-        const uint64_t a = g * 16 + (uint64_t)(NLOOK - 1 - bit) * S;
-        const uint8_t *t = A.text + a;
-        uint32_t lo = 0, hi = 0;
-        for (uint32_t i = 0; i < A.w; i++)
-        {
-            if (i < 4) lo |= (uint32_t)t[i] << (8 * i);
-            else hi |= (uint32_t)t[i] << (8 * (i - 4));
-        }
-        n += ac_probe(A, a, lo & A.fold, hi & A.fold);
-    }
-    return n;
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
 }
 
-// One 16-byte group: 16/S bitmap lookups.  Per lookup: window extraction (free for word-aligned windows,
-// two PRMT/SHF otherwise), hash = lo*M1 + hi*M2 on the FMA pipe (the multipliers' low zero bytes mask the
-// window to w bytes for free), bitmap byte address = mulhi(hash, bitmap_bytes) & ~3 (well-mixed high hash
-// bits), bit index = low hash bits (shifted for w < 4), one LDS.
-template <int S, bool FOLD>
-__device__ __forceinline__ uint32_t ac_group_hits(const uint32_t *s_bitmap, uint4 v, uint2 nx, uint32_t fold, uint32_t m1,
-                                                  uint32_t m2, uint32_t nbytes, uint32_t bit_shift)
+// The filter for one 16-byte group: 16/S bitmap lookups.  Per lookup:
+//   window extraction   free for word-aligned windows, two funnel shifts otherwise            (ALU)
+//   hash = lo*M1 + hi*M2   the multipliers' low zero bytes mask the window to w bytes for free  (FMA pipe)
+//   byte address = mulhi(hash, bitmap_bytes) + smem base   (well-mixed high hash bits)         (FMA pipe)
+//   one LDS.U8; the byte is replicated x4 (v * 0x01010101) so that a wrapping shift by the low   (LSU, FMA)
+//   hash bits selects bit (hash & 7) without masking; results are OR-ed                          (ALU x2)
+// DETAIL=false returns only "some lookup hit" in bit 0; DETAIL=true returns one bit per lookup
+// (first lookup = highest bit) and is used by the rare path only.
+template <int S, bool FOLD, bool DETAIL>
+__device__ __forceinline__ uint32_t ac_group_filter(uint32_t sbase, uint4 v, uint2 nx, uint32_t fold, uint32_t m1,
+                                                    uint32_t m2, uint32_t nbytes, uint32_t bit_shift)
 {
     uint32_t w[6] = {v.x, v.y, v.z, v.w, nx.x, nx.y};
     if (FOLD)
@@ -170,7 +157,7 @@ __device__ __forceinline__ uint32_t ac_group_hits(const uint32_t *s_bitmap, uint
 #pragma unroll
         for (int i = 0; i < 6; i++) w[i] &= fold;
     }
-    uint32_t hits = 0;
+    uint32_t acc = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++)
 #pragma unroll
@@ -179,31 +166,91 @@ __device__ __forceinline__ uint32_t ac_group_hits(const uint32_t *s_bitmap, uint
             const uint32_t lo = r == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * r);
             const uint32_t hi = r == 0 ? w[k + 1] : __funnelshift_r(w[k + 1], w[k + 2], 8 * r);
             const uint32_t h = lo * m1 + hi * m2;
-            const uint32_t addr = __umulhi(h, nbytes) & ~3u;
-            const uint32_t word = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_bitmap) + addr);
+            const uint32_t byte = lds_u8(__umulhi(h, nbytes) + sbase);
             const uint32_t sel = S == 1 ? (h >> bit_shift) : h;
-            hits = hits * 2 + (__funnelshift_r(word, 0, sel) & 1u);
+            const uint32_t t = __funnelshift_r(byte * 0x01010101u, 0u, sel);
+            if (DETAIL) acc = acc * 2 + (t & 1u);
+            else acc |= t;
         }
-    return hits;
+    return DETAIL ? acc : (acc & 1u);
 }
+
+// window value (lo,hi canonical: folded + masked to w bytes) -> exact table -> verify
+// (ac_probe above).  Rare path for one queued group: redo the lookups with per-lookup detail, rebuild the
+// canonical window of each hit from the same registers and probe the exact table.
+template <int S, bool FOLD>
+__device__ __noinline__ unsigned ac_process_group(const AcDev &A, uint32_t sbase, uint64_t g)
+{
+    const uint4 *t4 = reinterpret_cast<const uint4 *>(A.text);
+    const uint4 v = __ldg(t4 + g);
+    const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(t4 + g + 1));
+    uint32_t hits = ac_group_filter<S, FOLD, true>(sbase, v, nx, A.fold, A.mul_lo, A.mul_hi, 1u << (A.B - 3), A.bit_shift);
+    constexpr int NLOOK = 16 / S;
+    const uint32_t w[6] = {v.x, v.y, v.z, v.w, nx.x, nx.y};
+    unsigned n = 0;
+    while (hits)
+    {
+        const int bit = 31 - __clz(hits);
+        hits &= ~(1u << bit);
+        const int o = (NLOOK - 1 - bit) * S; // byte offset of the window inside the group
+        const int k = o >> 2, r = o & 3;
+        uint32_t lo = w[0], hi = w[1], h2 = w[2];
+#pragma unroll
+        for (int j = 1; j < 4; j++)
+            if (k == j) { lo = w[j]; hi = w[j + 1]; h2 = w[j + 2 < 6 ? j + 2 : 5]; }
+        if (r)
+        {
+            lo = __funnelshift_r(lo, hi, 8 * r);
+            hi = __funnelshift_r(hi, h2, 8 * r);
+        }
+        n += ac_probe(A, g * 16 + o, lo & A.fold & A.wmask_lo, hi & A.fold & A.wmask_hi);
+    }
+    return n;
+}
+
+static constexpr int AC_QW = 64; // per-warp candidate queue entries
 
 template <int S, bool FOLD>
 __global__ void __launch_bounds__(1024, 1) k_ac_scan(const __grid_constant__ AcDev A)
 {
-    extern __shared__ uint32_t s_bitmap[];
+    extern __shared__ __align__(16) uint8_t s_mem[];
+    uint32_t *s_bitmap = reinterpret_cast<uint32_t *>(s_mem);
+    const uint32_t nbytes = 1u << (A.B - 3);
+    uint64_t *s_q = reinterpret_cast<uint64_t *>(s_mem + nbytes) + (threadIdx.x >> 5) * AC_QW; // this warp's queue
     {
-        const uint32_t words = 1u << (A.B - 5);
         const uint4 *src = reinterpret_cast<const uint4 *>(A.bitmap);
         uint4 *dst = reinterpret_cast<uint4 *>(s_bitmap);
-        for (uint32_t i = threadIdx.x; i < words / 4; i += blockDim.x) dst[i] = src[i];
+        for (uint32_t i = threadIdx.x; i < nbytes / 16; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_bitmap);
     const uint4 *__restrict__ t4 = reinterpret_cast<const uint4 *>(A.text);
-    const uint32_t fold = A.fold, m1 = A.mul_lo, m2 = A.mul_hi, nbytes = 1u << (A.B - 3), bit_shift = A.bit_shift;
+    const uint32_t fold = A.fold, m1 = A.mul_lo, m2 = A.mul_hi, bit_shift = A.bit_shift;
+    const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1;
     unsigned long long local_cnt = 0;
+    uint32_t qn = 0; // warp-uniform
     constexpr int UNROLL = 2;
     const uint64_t tile = (uint64_t)blockDim.x * UNROLL;
     const uint64_t stride = (uint64_t)gridDim.x * tile;
+
+    // Candidate groups are parked in this warp's shared-memory queue (ballot + prefix popcount, no atomics)
+    // and verified 32 at a time by the whole warp, so the streaming loop never diverges into the slow path.
+    auto park = [&](uint32_t hit, uint64_t g) {
+        const uint32_t m = __ballot_sync(0xffffffffu, hit != 0);
+        if (m)
+        {
+            if (hit) s_q[qn + __popc(m & lt_mask)] = g;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn > AC_QW - 32)
+            {
+                for (uint32_t i = lane; i < qn; i += 32) local_cnt += ac_process_group<S, FOLD>(A, sbase, s_q[i]);
+                qn = 0;
+                __syncwarp();
+            }
+        }
+    };
+
     uint64_t g0 = A.group_begin + (uint64_t)blockIdx.x * tile;
     for (; g0 + tile <= A.group_end; g0 += stride)
     {
@@ -216,27 +263,29 @@ __global__ void __launch_bounds__(1024, 1) k_ac_scan(const __grid_constant__ AcD
             v[u] = __ldcs(q);
             nx[u] = __ldg(reinterpret_cast<const uint2 *>(q + 1)); // 8 bytes after the vector (in bounds by group_end)
         }
+        uint32_t hit[UNROLL]; // all filters first: nothing wide stays live across the (rare) parking path
 #pragma unroll
         for (int u = 0; u < UNROLL; u++)
-        {
-            const uint32_t hits = ac_group_hits<S, FOLD>(s_bitmap, v[u], nx[u], fold, m1, m2, nbytes, bit_shift);
-            if (hits) local_cnt += ac_detour<S>(A, g0 + (uint64_t)u * blockDim.x + threadIdx.x, hits);
-        }
+            hit[u] = ac_group_filter<S, FOLD, false>(sbase, v[u], nx[u], fold, m1, m2, nbytes, bit_shift);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) park(hit[u], g0 + (uint64_t)u * blockDim.x + threadIdx.x);
     }
-    if (g0 < A.group_end)
+    if (g0 < A.group_end) // ragged tile: whole warps stay converged (inactive lanes report no hit)
     {
         for (int u = 0; u < UNROLL; u++)
         {
             const uint64_t g = g0 + (uint64_t)u * blockDim.x + threadIdx.x;
+            uint32_t hit = 0;
             if (g < A.group_end)
             {
                 const uint4 v = __ldcs(t4 + g);
                 const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(t4 + g + 1));
-                const uint32_t hits = ac_group_hits<S, FOLD>(s_bitmap, v, nx, fold, m1, m2, nbytes, bit_shift);
-                if (hits) local_cnt += ac_detour<S>(A, g, hits);
+                hit = ac_group_filter<S, FOLD, false>(sbase, v, nx, fold, m1, m2, nbytes, bit_shift);
             }
+            park(hit, g);
         }
     }
+    for (uint32_t i = lane; i < qn; i += 32) local_cnt += ac_process_group<S, FOLD>(A, sbase, s_q[i]);
     // tail: occurrences whose sampled window lies beyond the vector loop — brute force, lanes over patterns
     if (blockIdx.x == 0 && threadIdx.x < 32)
     {
@@ -349,8 +398,9 @@ int ac_build_tables(Plan *plan)
         while (j < ents.size() && ents[j].key == ents[i].key) { list[j] = ents[j].e; j++; }
         const uint32_t lo = (uint32_t)ents[i].key, hi = (uint32_t)(ents[i].key >> 32);
         const uint32_t hsh = lo * T->mul_lo + hi * T->mul_hi;
-        const uint32_t addr = (uint32_t)(((uint64_t)hsh * (1u << (B - 3))) >> 32) & ~3u;
-        bitmap[addr >> 2] |= 1u << ((s == 1 ? (hsh >> T->bit_shift) : hsh) & 31);
+        const uint32_t baddr = (uint32_t)(((uint64_t)hsh * (1u << (B - 3))) >> 32); // byte address in the bitmap
+        const uint32_t bit = (s == 1 ? (hsh >> T->bit_shift) : hsh) & 7;
+        bitmap[baddr >> 2] |= 1u << (8 * (baddr & 3) + bit);
         uint32_t h = slot_hash(lo, hi) & (nslots - 1);
         while (slots[h].count) h = (h + 1) & (nslots - 1);
         slots[h] = AcSlot{ents[i].key, (uint32_t)i, (uint32_t)(j - i)};
@@ -444,14 +494,14 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_ac_scan<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        cudaFuncSetAttribute(k_ac_scan<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        cudaFuncSetAttribute(k_ac_scan<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        cudaFuncSetAttribute(k_ac_scan<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        cudaFuncSetAttribute(k_ac_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        cudaFuncSetAttribute(k_ac_scan<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_ac_scan<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     }
-    const size_t smem = (size_t)4 << (T->B - 5);
+    const size_t smem = ((size_t)4 << (T->B - 5)) + 32 * AC_QW * sizeof(uint64_t);
     const uint64_t groups = A.group_end - A.group_begin;
     uint64_t blocks = (groups + 2047) / 2048;
     if (blocks == 0) blocks = 1;
