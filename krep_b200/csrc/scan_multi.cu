@@ -44,7 +44,7 @@ struct AcDevTables
     uint32_t B = 0, nslots = 0, w = 0, s = 0, npat = 0;
     uint64_t wmask = 0; // low w bytes
     uint32_t fold = 0xFFFFFFFFu;
-    uint32_t mul_lo = 0, mul_hi = 0, bit_shift = 0;
+    uint32_t mul_lo = 0, mul_hi = 0, mul_b = 0, bit_shift = 0;
 };
 
 struct AcDev
@@ -56,7 +56,7 @@ struct AcDev
     const uint32_t *pat_off, *pat_len;
     uint32_t B, nslots, w, npat;
     uint32_t wmask_lo, wmask_hi, fold;
-    uint32_t mul_lo, mul_hi, bit_shift; // hash multipliers (low zero bytes mask the window), bit-index shift for w < 4
+    uint32_t mul_lo, mul_hi, mul_b, bit_shift; // hash multipliers (low zero bytes mask the window), bit-index shift for w < 4
     // launch
     const uint8_t *text;
     uint64_t avail_len, own_begin, own_end, global_offset;
@@ -175,6 +175,44 @@ __device__ __forceinline__ uint32_t ac_group_filter(uint32_t sbase, uint4 v, uin
     return DETAIL ? acc : (acc & 1u);
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+// S == 2 (w = 4 or 5): PAIRED lookups.  The shared-memory gather is the scarce resource (a random warp-wide
+// LDS costs ~3.5 bank-conflict wavefronts on the one-wavefront-per-cycle L1 data pipe), so the windows at a
+// and a+2 share ONE load: they overlap in T = bytes [a+2, a+w), which picks the 32-bit bitmap word; the two
+// bytes only window A has pick one of the word's low 16 bits, the two bytes only window B has pick one of its
+// high 16 bits.  Every pattern window is therefore entered twice at build time (A view: word by its last w-2
+// bytes, bit by its first 2; B view: word by its first w-2 bytes, bit by its last 2).  All hashing runs on the
+// FMA pipe (multipliers with low zero bytes mask for free; mulhi by 16 extracts the top 4 hash bits).
+template <bool FOLD, bool DETAIL>
+__device__ __forceinline__ uint32_t ac_pair_filter(uint32_t sbase, uint4 v, uint32_t nx0, uint32_t fold, uint32_t mT,
+                                                   uint32_t mA, uint32_t mB, uint32_t nbytes)
+{
+    uint32_t w[5] = {v.x, v.y, v.z, v.w, nx0};
+    if (FOLD)
+    {
+#pragma unroll
+        for (int i = 0; i < 5; i++) w[i] &= fold;
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        const uint32_t x = __funnelshift_r(w[k], w[k + 1], 16);              // bytes a+2 .. a+5
+        const uint32_t word = lds_u32((__umulhi(x * mT, nbytes) + sbase) & ~3u);
+        const uint32_t tA = __funnelshift_r(word, 0u, __umulhi(w[k] * mA, 16u));          // bit 0..15
+        const uint32_t tB = __funnelshift_r(word, 0u, __umulhi(w[k + 1] * mB, 16u) + 16u); // bit 16..31
+        if (DETAIL) acc = acc * 4 + (tA & 1u) * 2 + (tB & 1u);
+        else acc |= tA | tB;
+    }
+    return DETAIL ? acc : (acc & 1u);
+}
+
 // window value (lo,hi canonical: folded + masked to w bytes) -> exact table -> verify
 // (ac_probe above).  Rare path for one queued group: redo the lookups with per-lookup detail, rebuild the
 // canonical window of each hit from the same registers and probe the exact table.
@@ -184,7 +222,11 @@ __device__ __noinline__ unsigned ac_process_group(const AcDev &A, uint32_t sbase
     const uint4 *t4 = reinterpret_cast<const uint4 *>(A.text);
     const uint4 v = __ldg(t4 + g);
     const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(t4 + g + 1));
-    uint32_t hits = ac_group_filter<S, FOLD, true>(sbase, v, nx, A.fold, A.mul_lo, A.mul_hi, 1u << (A.B - 3), A.bit_shift);
+    uint32_t hits;
+    if constexpr (S == 2)
+        hits = ac_pair_filter<FOLD, true>(sbase, v, nx.x, A.fold, A.mul_lo, A.mul_hi, A.mul_b, 1u << (A.B - 3));
+    else
+        hits = ac_group_filter<S, FOLD, true>(sbase, v, nx, A.fold, A.mul_lo, A.mul_hi, 1u << (A.B - 3), A.bit_shift);
     constexpr int NLOOK = 16 / S;
     const uint32_t w[6] = {v.x, v.y, v.z, v.w, nx.x, nx.y};
     unsigned n = 0;
@@ -251,38 +293,44 @@ __global__ void __launch_bounds__(1024, 1) k_ac_scan(const __grid_constant__ AcD
         }
     };
 
+    const uint32_t m3 = A.mul_b;
+    // one group through the filter; for S == 2 the word after the vector comes from the next lane's registers
+    auto filter = [&](const uint4 *q, const uint4 &v) -> uint32_t {
+        if constexpr (S == 2)
+        {
+            uint32_t nx0 = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (lane == 31) nx0 = __ldg(reinterpret_cast<const uint32_t *>(q + 1));
+            return ac_pair_filter<FOLD, false>(sbase, v, nx0, fold, m1, m2, m3, nbytes);
+        }
+        else
+        {
+            const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(q + 1)); // 8 bytes after the vector (in bounds by group_end)
+            return ac_group_filter<S, FOLD, false>(sbase, v, nx, fold, m1, m2, nbytes, bit_shift);
+        }
+    };
     uint64_t g0 = A.group_begin + (uint64_t)blockIdx.x * tile;
     for (; g0 + tile <= A.group_end; g0 += stride)
     {
         uint4 v[UNROLL];
-        uint2 nx[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++)
-        {
-            const uint4 *q = t4 + g0 + (uint64_t)u * blockDim.x + threadIdx.x;
-            v[u] = __ldcs(q);
-            nx[u] = __ldg(reinterpret_cast<const uint2 *>(q + 1)); // 8 bytes after the vector (in bounds by group_end)
-        }
+        for (int u = 0; u < UNROLL; u++) v[u] = __ldcs(t4 + g0 + (uint64_t)u * blockDim.x + threadIdx.x);
         uint32_t hit[UNROLL]; // all filters first: nothing wide stays live across the (rare) parking path
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++)
-            hit[u] = ac_group_filter<S, FOLD, false>(sbase, v[u], nx[u], fold, m1, m2, nbytes, bit_shift);
+        for (int u = 0; u < UNROLL; u++) hit[u] = filter(t4 + g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u]);
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) park(hit[u], g0 + (uint64_t)u * blockDim.x + threadIdx.x);
     }
-    if (g0 < A.group_end) // ragged tile: whole warps stay converged (inactive lanes report no hit)
+    if (g0 < A.group_end) // ragged tile: whole warps stay converged (lanes past the end load the last group, report no hit)
     {
         for (int u = 0; u < UNROLL; u++)
         {
             const uint64_t g = g0 + (uint64_t)u * blockDim.x + threadIdx.x;
-            uint32_t hit = 0;
-            if (g < A.group_end)
-            {
-                const uint4 v = __ldcs(t4 + g);
-                const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(t4 + g + 1));
-                hit = ac_group_filter<S, FOLD, false>(sbase, v, nx, fold, m1, m2, nbytes, bit_shift);
-            }
-            park(hit, g);
+            const uint64_t gc = g < A.group_end ? g : A.group_end - 1;
+            const uint4 v = __ldcs(t4 + gc);
+            uint32_t hit = filter(t4 + gc, v);
+            if (S == 2 && g + 1 == A.group_end && lane != 31) // neighbour lane holds a clamped group: reload the true next word
+                hit = ac_pair_filter<FOLD, false>(sbase, v, __ldg(reinterpret_cast<const uint32_t *>(t4 + gc + 1)), fold, m1, m2, m3, nbytes);
+            park(g < A.group_end ? hit : 0u, g);
         }
     }
     for (uint32_t i = lane; i < qn; i += 32) local_cnt += ac_process_group<S, FOLD>(A, sbase, s_q[i]);
@@ -358,6 +406,12 @@ int ac_build_tables(Plan *plan)
     T->mul_lo = w >= 4 ? HC1 : (HC1 << (8 * (4 - w)));
     T->mul_hi = w > 4 ? (w >= 8 ? HC2 : (HC2 << (8 * (8 - w)))) : 0u;
     T->bit_shift = w >= 4 ? 0u : 8 * (4 - w);
+    if (s == 2) // paired scheme (ac_pair_filter): mT masks T to w-2 bytes, mA to 2 bytes, mB to w-2 bytes
+    {
+        T->mul_lo = HC1 << (8 * (4 - (w - 2)));
+        T->mul_hi = HC2 << 16;
+        T->mul_b = 0xC2B2AE35u << (8 * (4 - (w - 2)));
+    }
 
     // pattern pool (exact compare data) + window entries
     std::vector<uint32_t> off(K), len(K);
@@ -397,10 +451,26 @@ int ac_build_tables(Plan *plan)
         size_t j = i;
         while (j < ents.size() && ents[j].key == ents[i].key) { list[j] = ents[j].e; j++; }
         const uint32_t lo = (uint32_t)ents[i].key, hi = (uint32_t)(ents[i].key >> 32);
-        const uint32_t hsh = lo * T->mul_lo + hi * T->mul_hi;
-        const uint32_t baddr = (uint32_t)(((uint64_t)hsh * (1u << (B - 3))) >> 32); // byte address in the bitmap
-        const uint32_t bit = (s == 1 ? (hsh >> T->bit_shift) : hsh) & 7;
-        bitmap[baddr >> 2] |= 1u << (8 * (baddr & 3) + bit);
+        if (s == 2)
+        {
+            // window bytes c0..c(w-1) as a 64-bit little-endian value
+            const uint64_t c = ents[i].key;
+            const uint32_t tl = w - 2, tmask = tl >= 4 ? 0xFFFFFFFFu : ((1u << (8 * tl)) - 1);
+            const uint32_t nby = 1u << (B - 3);
+            auto word_of = [&](uint32_t t) { return (uint32_t)(((uint64_t)(t * T->mul_lo) * nby) >> 32) >> 2; };
+            auto top4 = [](uint32_t x) { return (uint32_t)(((uint64_t)x * 16u) >> 32); };
+            const uint32_t first2 = (uint32_t)(c & 0xFFFF), lastT = (uint32_t)(c >> 16) & tmask;
+            const uint32_t firstT = (uint32_t)c & tmask;
+            bitmap[word_of(lastT)] |= 1u << top4(first2 * T->mul_hi);               // A view
+            bitmap[word_of(firstT)] |= 1u << (16 + top4(lastT * T->mul_b));          // B view (bytes 2..w-1)
+        }
+        else
+        {
+            const uint32_t hsh = lo * T->mul_lo + hi * T->mul_hi;
+            const uint32_t baddr = (uint32_t)(((uint64_t)hsh * (1u << (B - 3))) >> 32); // byte address in the bitmap
+            const uint32_t bit = (s == 1 ? (hsh >> T->bit_shift) : hsh) & 7;
+            bitmap[baddr >> 2] |= 1u << (8 * (baddr & 3) + bit);
+        }
         uint32_t h = slot_hash(lo, hi) & (nslots - 1);
         while (slots[h].count) h = (h + 1) & (nslots - 1);
         slots[h] = AcSlot{ents[i].key, (uint32_t)i, (uint32_t)(j - i)};
@@ -468,6 +538,7 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     A.mul_lo = T->mul_lo;
     A.mul_hi = T->mul_hi;
     A.bit_shift = T->bit_shift;
+    A.mul_b = T->mul_b;
     A.text = a.text;
     A.avail_len = a.avail_len;
     A.own_begin = a.own_begin;
