@@ -54,7 +54,7 @@ struct AcDev
     const uint32_t *list;
     const uint8_t *pool_val, *pool_mask;
     const uint32_t *pat_off, *pat_len;
-    uint32_t B, nslots, w, npat;
+    uint32_t B, nslots, w, npat, bitmap_bytes;
     uint32_t wmask_lo, wmask_hi, fold;
     uint32_t mul_lo, mul_hi, mul_b, bit_shift; // hash multipliers (low zero bytes mask the window), bit-index shift for w < 4
     // launch
@@ -148,7 +148,7 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
 // DETAIL=false returns only "some lookup hit" in bit 0; DETAIL=true returns one bit per lookup
 // (first lookup = highest bit) and is used by the rare path only.
 template <int S, bool FOLD, bool DETAIL>
-__device__ __forceinline__ uint32_t ac_group_filter(uint32_t sbase, uint4 v, uint2 nx, uint32_t fold, uint32_t m1,
+__device__ __forceinline__ uint32_t ac_group_filter(const uint8_t *s_mem, uint4 v, uint2 nx, uint32_t fold, uint32_t m1,
                                                     uint32_t m2, uint32_t nbytes, uint32_t bit_shift)
 {
     uint32_t w[6] = {v.x, v.y, v.z, v.w, nx.x, nx.y};
@@ -166,7 +166,7 @@ __device__ __forceinline__ uint32_t ac_group_filter(uint32_t sbase, uint4 v, uin
             const uint32_t lo = r == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * r);
             const uint32_t hi = r == 0 ? w[k + 1] : __funnelshift_r(w[k + 1], w[k + 2], 8 * r);
             const uint32_t h = lo * m1 + hi * m2;
-            const uint32_t byte = lds_u8(__umulhi(h, nbytes) + sbase);
+            const uint32_t byte = s_mem[__umulhi(h, nbytes)];
             const uint32_t sel = S == 1 ? (h >> bit_shift) : h;
             const uint32_t t = __funnelshift_r(byte * 0x01010101u, 0u, sel);
             if (DETAIL) acc = acc * 2 + (t & 1u);
@@ -190,7 +190,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
 // bytes, bit by its first 2; B view: word by its first w-2 bytes, bit by its last 2).  All hashing runs on the
 // FMA pipe (multipliers with low zero bytes mask for free; mulhi by 16 extracts the top 4 hash bits).
 template <bool FOLD, bool DETAIL>
-__device__ __forceinline__ uint32_t ac_pair_filter(uint32_t sbase, uint4 v, uint32_t nx0, uint32_t fold, uint32_t mT,
+__device__ __forceinline__ uint32_t ac_pair_filter(const uint8_t *s_mem, uint4 v, uint32_t nx0, uint32_t fold, uint32_t mT,
                                                    uint32_t mA, uint32_t mB, uint32_t nbytes)
 {
     uint32_t w[5] = {v.x, v.y, v.z, v.w, nx0};
@@ -204,7 +204,7 @@ __device__ __forceinline__ uint32_t ac_pair_filter(uint32_t sbase, uint4 v, uint
     for (int k = 0; k < 4; k++)
     {
         const uint32_t x = __funnelshift_r(w[k], w[k + 1], 16);              // bytes a+2 .. a+5
-        const uint32_t word = lds_u32((__umulhi(x * mT, nbytes) + sbase) & ~3u);
+        const uint32_t word = *reinterpret_cast<const uint32_t *>(s_mem + (__umulhi(x * mT, nbytes) & ~3u));
         const uint32_t tA = __funnelshift_r(word, 0u, __umulhi(w[k] * mA, 16u));          // bit 0..15
         const uint32_t tB = __funnelshift_r(word, 0u, __umulhi(w[k + 1] * mB, 16u) + 16u); // bit 16..31
         if (DETAIL) acc = acc * 4 + (tA & 1u) * 2 + (tB & 1u);
@@ -213,127 +213,172 @@ __device__ __forceinline__ uint32_t ac_pair_filter(uint32_t sbase, uint4 v, uint
     return DETAIL ? acc : (acc & 1u);
 }
 
-// window value (lo,hi canonical: folded + masked to w bytes) -> exact table -> verify
-// (ac_probe above).  Rare path for one queued group: redo the lookups with per-lookup detail, rebuild the
-// canonical window of each hit from the same registers and probe the exact table.
+// ---------------------------------------------------------------------------------------------
+// Rare path.  Candidate groups parked by the streaming loop are verified 32 at a time, one group per
+// lane, in warp-synchronous loops (every lane pops one hit, then all lanes step their hash-table probe
+// together), so the slow path keeps the whole warp busy instead of trailing single lanes.
+// ---------------------------------------------------------------------------------------------
 template <int S, bool FOLD>
-__device__ __noinline__ unsigned ac_process_group(const AcDev &A, uint32_t sbase, uint64_t g)
+__device__ __noinline__ unsigned ac_verify_groups(const AcDev &A, const uint8_t *s_mem, uint64_t g, bool valid)
 {
     const uint4 *t4 = reinterpret_cast<const uint4 *>(A.text);
-    const uint4 v = __ldg(t4 + g);
-    const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(t4 + g + 1));
-    uint32_t hits;
-    if constexpr (S == 2)
-        hits = ac_pair_filter<FOLD, true>(sbase, v, nx.x, A.fold, A.mul_lo, A.mul_hi, A.mul_b, 1u << (A.B - 3));
-    else
-        hits = ac_group_filter<S, FOLD, true>(sbase, v, nx, A.fold, A.mul_lo, A.mul_hi, 1u << (A.B - 3), A.bit_shift);
-    constexpr int NLOOK = 16 / S;
-    const uint32_t w[6] = {v.x, v.y, v.z, v.w, nx.x, nx.y};
-    unsigned n = 0;
-    while (hits)
+    uint32_t hits = 0;
+    uint32_t w[6] = {0, 0, 0, 0, 0, 0};
+    if (valid)
     {
-        const int bit = 31 - __clz(hits);
-        hits &= ~(1u << bit);
-        const int o = (NLOOK - 1 - bit) * S; // byte offset of the window inside the group
-        const int k = o >> 2, r = o & 3;
-        uint32_t lo = w[0], hi = w[1], h2 = w[2];
-#pragma unroll
-        for (int j = 1; j < 4; j++)
-            if (k == j) { lo = w[j]; hi = w[j + 1]; h2 = w[j + 2 < 6 ? j + 2 : 5]; }
-        if (r)
+        const uint4 v = __ldg(t4 + g);
+        const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(t4 + g + 1));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; w[4] = nx.x; w[5] = nx.y;
+        if constexpr (S == 2)
+            hits = ac_pair_filter<FOLD, true>(s_mem, v, nx.x, A.fold, A.mul_lo, A.mul_hi, A.mul_b, A.bitmap_bytes);
+        else
+            hits = ac_group_filter<S, FOLD, true>(s_mem, v, nx, A.fold, A.mul_lo, A.mul_hi, A.bitmap_bytes, A.bit_shift);
+    }
+    constexpr int NLOOK = 16 / S;
+    unsigned n = 0;
+    while (__any_sync(0xffffffffu, hits != 0))
+    {
+        bool active = hits != 0;
+        uint64_t key = 0, a = 0;
+        uint32_t h = 0;
+        if (active)
         {
-            lo = __funnelshift_r(lo, hi, 8 * r);
-            hi = __funnelshift_r(hi, h2, 8 * r);
+            const int bit = 31 - __clz(hits);
+            hits &= ~(1u << bit);
+            const int o = (NLOOK - 1 - bit) * S; // byte offset of the window inside the group
+            const int k = o >> 2, r = o & 3;
+            uint32_t lo = w[0], hi = w[1], h2 = w[2];
+#pragma unroll
+            for (int j = 1; j < 4; j++)
+                if (k == j) { lo = w[j]; hi = w[j + 1]; h2 = w[j + 2 < 6 ? j + 2 : 5]; }
+            if (r)
+            {
+                lo = __funnelshift_r(lo, hi, 8 * r);
+                hi = __funnelshift_r(hi, h2, 8 * r);
+            }
+            lo &= A.fold & A.wmask_lo;
+            hi &= A.fold & A.wmask_hi;
+            key = ((uint64_t)hi << 32) | lo;
+            h = slot_hash(lo, hi) & (A.nslots - 1);
+            a = g * 16 + o;
         }
-        n += ac_probe(A, g * 16 + o, lo & A.fold & A.wmask_lo, hi & A.fold & A.wmask_hi);
+        while (__any_sync(0xffffffffu, active))
+        {
+            if (active)
+            {
+                const AcSlot sl = A.slots[h];
+                if (sl.count == 0) active = false;
+                else if (sl.key == key)
+                {
+                    for (uint32_t i = 0; i < sl.count; i++)
+                    {
+                        const uint32_t e = A.list[sl.first + i];
+                        n += ac_verify_emit(A, e >> 2, (long long)a - (long long)(e & 3));
+                    }
+                    active = false;
+                }
+                else h = (h + 1) & (A.nslots - 1);
+            }
+        }
     }
     return n;
 }
 
-static constexpr int AC_QW = 64; // per-warp candidate queue entries
+template <int UNROLL>
+struct AcQueue
+{
+    static constexpr int CAP = 32 * UNROLL + 32; // a remainder of < 32 plus one full iteration of new candidates
+};
 
-template <int S, bool FOLD>
-__global__ void __launch_bounds__(1024, 1) k_ac_scan(const __grid_constant__ AcDev A)
+template <int S, bool FOLD, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ AcDev A)
 {
     extern __shared__ __align__(16) uint8_t s_mem[];
-    uint32_t *s_bitmap = reinterpret_cast<uint32_t *>(s_mem);
-    const uint32_t nbytes = 1u << (A.B - 3);
-    uint64_t *s_q = reinterpret_cast<uint64_t *>(s_mem + nbytes) + (threadIdx.x >> 5) * AC_QW; // this warp's queue
+    constexpr int QCAP = AcQueue<UNROLL>::CAP;
+    const uint32_t nbytes = A.bitmap_bytes;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_mem + nbytes) + warp; // this warp's queue length
+    uint64_t *s_q = reinterpret_cast<uint64_t *>(s_mem + nbytes + 128) + warp * QCAP;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(A.bitmap);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_bitmap);
-        for (uint32_t i = threadIdx.x; i < nbytes / 16; i += blockDim.x) dst[i] = src[i];
+        uint4 *dst = reinterpret_cast<uint4 *>(s_mem);
+        for (uint32_t i = threadIdx.x; i < nbytes / 16; i += THREADS) dst[i] = src[i];
+        if (lane == 0) *s_cnt = 0;
     }
     __syncthreads();
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_bitmap);
     const uint4 *__restrict__ t4 = reinterpret_cast<const uint4 *>(A.text);
-    const uint32_t fold = A.fold, m1 = A.mul_lo, m2 = A.mul_hi, bit_shift = A.bit_shift;
-    const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1;
+    const uint32_t fold = A.fold, m1 = A.mul_lo, m2 = A.mul_hi, m3 = A.mul_b, bit_shift = A.bit_shift;
     unsigned long long local_cnt = 0;
-    uint32_t qn = 0; // warp-uniform
-    constexpr int UNROLL = 2;
-    const uint64_t tile = (uint64_t)blockDim.x * UNROLL;
+    constexpr uint64_t tile = (uint64_t)THREADS * UNROLL;
     const uint64_t stride = (uint64_t)gridDim.x * tile;
 
-    // Candidate groups are parked in this warp's shared-memory queue (ballot + prefix popcount, no atomics)
-    // and verified 32 at a time by the whole warp, so the streaming loop never diverges into the slow path.
-    auto park = [&](uint32_t hit, uint64_t g) {
-        const uint32_t m = __ballot_sync(0xffffffffu, hit != 0);
-        if (m)
-        {
-            if (hit) s_q[qn + __popc(m & lt_mask)] = g;
-            qn += __popc(m);
-            __syncwarp();
-            if (qn > AC_QW - 32)
-            {
-                for (uint32_t i = lane; i < qn; i += 32) local_cnt += ac_process_group<S, FOLD>(A, sbase, s_q[i]);
-                qn = 0;
-                __syncwarp();
-            }
-        }
-    };
-
-    const uint32_t m3 = A.mul_b;
     // one group through the filter; for S == 2 the word after the vector comes from the next lane's registers
     auto filter = [&](const uint4 *q, const uint4 &v) -> uint32_t {
         if constexpr (S == 2)
         {
             uint32_t nx0 = __shfl_down_sync(0xffffffffu, v.x, 1);
             if (lane == 31) nx0 = __ldg(reinterpret_cast<const uint32_t *>(q + 1));
-            return ac_pair_filter<FOLD, false>(sbase, v, nx0, fold, m1, m2, m3, nbytes);
+            return ac_pair_filter<FOLD, false>(s_mem, v, nx0, fold, m1, m2, m3, nbytes);
         }
         else
         {
             const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(q + 1)); // 8 bytes after the vector (in bounds by group_end)
-            return ac_group_filter<S, FOLD, false>(sbase, v, nx, fold, m1, m2, nbytes, bit_shift);
+            return ac_group_filter<S, FOLD, false>(s_mem, v, nx, fold, m1, m2, nbytes, bit_shift);
         }
     };
+    // Candidate groups are parked in this warp's shared-memory queue and verified 32 at a time.
+    auto park = [&](uint32_t hit, uint64_t g) {
+        if (hit) s_q[atomicAdd(s_cnt, 1u)] = g;
+    };
+    auto drain = [&](bool all) {
+        __syncwarp();
+        uint32_t c = *reinterpret_cast<volatile uint32_t *>(s_cnt);
+        if (c >= 32 || (all && c))
+        {
+            while (c >= 32)
+            {
+                c -= 32;
+                local_cnt += ac_verify_groups<S, FOLD>(A, s_mem, s_q[c + lane], true);
+            }
+            if (all && c)
+            {
+                local_cnt += ac_verify_groups<S, FOLD>(A, s_mem, lane < c ? s_q[lane] : 0, lane < c);
+                c = 0;
+            }
+            __syncwarp();
+            if (lane == 0) *s_cnt = c;
+            __syncwarp();
+        }
+    };
+
     uint64_t g0 = A.group_begin + (uint64_t)blockIdx.x * tile;
     for (; g0 + tile <= A.group_end; g0 += stride)
     {
         uint4 v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) v[u] = __ldcs(t4 + g0 + (uint64_t)u * blockDim.x + threadIdx.x);
-        uint32_t hit[UNROLL]; // all filters first: nothing wide stays live across the (rare) parking path
+        for (int u = 0; u < UNROLL; u++) v[u] = __ldcs(t4 + g0 + (uint64_t)u * THREADS + threadIdx.x);
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) hit[u] = filter(t4 + g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u]);
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) park(hit[u], g0 + (uint64_t)u * blockDim.x + threadIdx.x);
+        for (int u = 0; u < UNROLL; u++)
+        {
+            const uint64_t g = g0 + (uint64_t)u * THREADS + threadIdx.x;
+            park(filter(t4 + g, v[u]), g);
+        }
+        drain(false);
     }
-    if (g0 < A.group_end) // ragged tile: whole warps stay converged (lanes past the end load the last group, report no hit)
+    if (g0 < A.group_end) // ragged tile: whole warps stay converged (lanes past the end re-read the last group, report no hit)
     {
         for (int u = 0; u < UNROLL; u++)
         {
-            const uint64_t g = g0 + (uint64_t)u * blockDim.x + threadIdx.x;
+            const uint64_t g = g0 + (uint64_t)u * THREADS + threadIdx.x;
             const uint64_t gc = g < A.group_end ? g : A.group_end - 1;
             const uint4 v = __ldcs(t4 + gc);
             uint32_t hit = filter(t4 + gc, v);
-            if (S == 2 && g + 1 == A.group_end && lane != 31) // neighbour lane holds a clamped group: reload the true next word
-                hit = ac_pair_filter<FOLD, false>(sbase, v, __ldg(reinterpret_cast<const uint32_t *>(t4 + gc + 1)), fold, m1, m2, m3, nbytes);
+            if (S == 2 && g + 1 == A.group_end && lane != 31) // the neighbour lane holds a clamped group: use the true next word
+                hit = ac_pair_filter<FOLD, false>(s_mem, v, __ldg(reinterpret_cast<const uint32_t *>(t4 + gc + 1)), fold, m1, m2, m3, nbytes);
             park(g < A.group_end ? hit : 0u, g);
         }
     }
-    for (uint32_t i = lane; i < qn; i += 32) local_cnt += ac_process_group<S, FOLD>(A, sbase, s_q[i]);
+    drain(true);
     // tail: occurrences whose sampled window lies beyond the vector loop — brute force, lanes over patterns
     if (blockIdx.x == 0 && threadIdx.x < 32)
     {
@@ -349,7 +394,7 @@ __global__ void __launch_bounds__(1024, 1) k_ac_scan(const __grid_constant__ AcD
     {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) local_cnt += __shfl_xor_sync(0xffffffffu, local_cnt, o);
-        if ((threadIdx.x & 31) == 0 && local_cnt) atomicAdd(A.counter, local_cnt);
+        if (lane == 0 && local_cnt) atomicAdd(A.counter, local_cnt);
     }
 }
 
@@ -529,6 +574,7 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     A.pat_off = T->d_pat_off;
     A.pat_len = T->d_pat_len;
     A.B = T->B;
+    A.bitmap_bytes = 1u << (T->B - 3);
     A.nslots = T->nslots;
     A.w = T->w;
     A.npat = T->npat;
@@ -559,33 +605,28 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     if (A.group_end > total_groups) A.group_end = total_groups;
     if (A.group_begin > A.group_end) A.group_begin = A.group_end;
 
+    constexpr int THREADS = 768, UNROLL = 4;
     static int sm_count = 0;
+    const size_t smem = ((size_t)1 << (T->B - 3)) + 128 + (size_t)(THREADS / 32) * AcQueue<UNROLL>::CAP * sizeof(uint64_t);
+    auto kernel = [&]() -> void (*)(AcDev) {
+        const bool f = T->fold != 0xFFFFFFFFu;
+        if (T->s == 1) return f ? k_ac_scan<1, true, THREADS, UNROLL> : k_ac_scan<1, false, THREADS, UNROLL>;
+        if (T->s == 2) return f ? k_ac_scan<2, true, THREADS, UNROLL> : k_ac_scan<2, false, THREADS, UNROLL>;
+        return f ? k_ac_scan<4, true, THREADS, UNROLL> : k_ac_scan<4, false, THREADS, UNROLL>;
+    }();
     if (!sm_count)
     {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_ac_scan<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_ac_scan<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_ac_scan<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_ac_scan<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_ac_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_ac_scan<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     }
-    const size_t smem = ((size_t)4 << (T->B - 5)) + 32 * AC_QW * sizeof(uint64_t);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const uint64_t groups = A.group_end - A.group_begin;
-    uint64_t blocks = (groups + 2047) / 2048;
+    const uint64_t tile = (uint64_t)THREADS * UNROLL;
+    uint64_t blocks = (groups + tile - 1) / tile;
     if (blocks == 0) blocks = 1;
-    const uint64_t resident = (uint64_t)sm_count * (smem <= 100 * 1024 ? 2 : 1); // 1024-thread CTAs
-    if (blocks > resident) blocks = resident;
-    const bool f = T->fold != 0xFFFFFFFFu;
-    const unsigned nb = (unsigned)blocks;
-    if (T->s == 1)
-        f ? k_ac_scan<1, true><<<nb, 1024, smem, st>>>(A) : k_ac_scan<1, false><<<nb, 1024, smem, st>>>(A);
-    else if (T->s == 2)
-        f ? k_ac_scan<2, true><<<nb, 1024, smem, st>>>(A) : k_ac_scan<2, false><<<nb, 1024, smem, st>>>(A);
-    else
-        f ? k_ac_scan<4, true><<<nb, 1024, smem, st>>>(A) : k_ac_scan<4, false><<<nb, 1024, smem, st>>>(A);
+    if (blocks > (uint64_t)sm_count) blocks = sm_count; // one resident CTA per SM (shared-memory bitmap)
+    kernel<<<(unsigned)blocks, THREADS, smem, st>>>(A);
     count_launch();
 }
 
