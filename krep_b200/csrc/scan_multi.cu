@@ -72,8 +72,12 @@ static constexpr uint32_t HC1 = 0x9E3779B1u, HC2 = 0x85EBCA77u;
 
 __host__ __device__ __forceinline__ uint32_t slot_hash(uint32_t lo, uint32_t hi)
 {
-    uint32_t h = (lo ^ (hi * 0xC2B2AE3Du)) * 0x27D4EB2Fu;
-    return h ^ (h >> 15);
+    uint32_t h = lo * 0x9E3779B1u + hi * 0x85EBCA77u; // murmur3-style finaliser: the table index uses the low bits
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    return h ^ (h >> 16);
 }
 
 __device__ __forceinline__ bool dev_is_word2(int c)
@@ -351,12 +355,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
         }
     };
 
+    // Register double buffering: the vectors of the next tile are requested before the current tile is
+    // filtered, so HBM latency overlaps this warp's own ~260 filter instructions (plus the other warps).
     uint64_t g0 = A.group_begin + (uint64_t)blockIdx.x * tile;
-    for (; g0 + tile <= A.group_end; g0 += stride)
+    uint4 v[UNROLL];
+    if (g0 + tile <= A.group_end)
     {
-        uint4 v[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) v[u] = __ldcs(t4 + g0 + (uint64_t)u * THREADS + threadIdx.x);
+    }
+    for (; g0 + tile <= A.group_end; g0 += stride)
+    {
+        uint4 vn[UNROLL];
+        const uint64_t gn = g0 + stride;
+        if (gn + tile <= A.group_end)
+        {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) vn[u] = __ldcs(t4 + gn + (uint64_t)u * THREADS + threadIdx.x);
+        }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++)
         {
@@ -364,6 +380,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
             park(filter(t4 + g, v[u]), g);
         }
         drain(false);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) v[u] = vn[u];
     }
     if (g0 < A.group_end) // ragged tile: whole warps stay converged (lanes past the end re-read the last group, report no hit)
     {
@@ -487,7 +505,7 @@ int ac_build_tables(Plan *plan)
     T->B = B;
     std::vector<uint32_t> bitmap(1u << (B - 5), 0);
     uint32_t nslots = 16;
-    while (nslots < 2 * distinct + 1) nslots *= 2;
+    while (nslots < 8 * distinct + 1) nslots *= 2; // load factor <= 1/8: a miss (the common case) ends after ~1.1 probes
     T->nslots = nslots;
     std::vector<AcSlot> slots(nslots, AcSlot{0, 0, 0});
     std::vector<uint32_t> list(ents.size());
@@ -605,7 +623,7 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     if (A.group_end > total_groups) A.group_end = total_groups;
     if (A.group_begin > A.group_end) A.group_begin = A.group_end;
 
-    constexpr int THREADS = 768, UNROLL = 4;
+    constexpr int THREADS = 640, UNROLL = 4;
     static int sm_count = 0;
     const size_t smem = ((size_t)1 << (T->B - 3)) + 128 + (size_t)(THREADS / 32) * AcQueue<UNROLL>::CAP * sizeof(uint64_t);
     auto kernel = [&]() -> void (*)(AcDev) {
