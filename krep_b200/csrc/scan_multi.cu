@@ -316,19 +316,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
     constexpr uint64_t tile = (uint64_t)THREADS * UNROLL;
     const uint64_t stride = (uint64_t)gridDim.x * tile;
 
-    // one group through the filter; for S == 2 the word after the vector comes from the next lane's registers
-    auto filter = [&](const uint4 *q, const uint4 &v) -> uint32_t {
+    // The 8 bytes that follow a group's vector: for S == 2 only one word is needed and it comes from the next
+    // lane's registers (shuffle), so only lane 31 loads it; other strides load it per lane.  Either way the load
+    // is issued together with the vector (prefetched), never in front of its use.
+    auto load_next = [&](const uint4 *q) -> uint2 {
+        if constexpr (S == 2)
+            return lane == 31 ? make_uint2(__ldg(reinterpret_cast<const uint32_t *>(q + 1)), 0u) : make_uint2(0u, 0u);
+        else
+            return __ldg(reinterpret_cast<const uint2 *>(q + 1)); // in bounds by group_end
+    };
+    auto filter = [&](const uint4 &v, const uint2 &nx) -> uint32_t {
         if constexpr (S == 2)
         {
             uint32_t nx0 = __shfl_down_sync(0xffffffffu, v.x, 1);
-            if (lane == 31) nx0 = __ldg(reinterpret_cast<const uint32_t *>(q + 1));
+            if (lane == 31) nx0 = nx.x;
             return ac_pair_filter<FOLD, false>(s_mem, v, nx0, fold, m1, m2, m3, nbytes);
         }
         else
-        {
-            const uint2 nx = __ldg(reinterpret_cast<const uint2 *>(q + 1)); // 8 bytes after the vector (in bounds by group_end)
             return ac_group_filter<S, FOLD, false>(s_mem, v, nx, fold, m1, m2, nbytes, bit_shift);
-        }
     };
     // Candidate groups are parked in this warp's shared-memory queue and verified 32 at a time.
     auto park = [&](uint32_t hit, uint64_t g) {
@@ -359,29 +364,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
     // filtered, so HBM latency overlaps this warp's own ~260 filter instructions (plus the other warps).
     uint64_t g0 = A.group_begin + (uint64_t)blockIdx.x * tile;
     uint4 v[UNROLL];
+    uint2 nx[UNROLL];
     if (g0 + tile <= A.group_end)
     {
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) v[u] = __ldcs(t4 + g0 + (uint64_t)u * THREADS + threadIdx.x);
+        for (int u = 0; u < UNROLL; u++)
+        {
+            const uint4 *q = t4 + g0 + (uint64_t)u * THREADS + threadIdx.x;
+            v[u] = __ldcs(q);
+            nx[u] = load_next(q);
+        }
     }
     for (; g0 + tile <= A.group_end; g0 += stride)
     {
         uint4 vn[UNROLL];
+        uint2 nxn[UNROLL];
         const uint64_t gn = g0 + stride;
         if (gn + tile <= A.group_end)
         {
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) vn[u] = __ldcs(t4 + gn + (uint64_t)u * THREADS + threadIdx.x);
+            for (int u = 0; u < UNROLL; u++)
+            {
+                const uint4 *q = t4 + gn + (uint64_t)u * THREADS + threadIdx.x;
+                vn[u] = __ldcs(q);
+                nxn[u] = load_next(q);
+            }
         }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) park(filter(v[u], nx[u]), g0 + (uint64_t)u * THREADS + threadIdx.x);
+        drain(false);
 #pragma unroll
         for (int u = 0; u < UNROLL; u++)
         {
-            const uint64_t g = g0 + (uint64_t)u * THREADS + threadIdx.x;
-            park(filter(t4 + g, v[u]), g);
+            v[u] = vn[u];
+            nx[u] = nxn[u];
         }
-        drain(false);
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) v[u] = vn[u];
     }
     if (g0 < A.group_end) // ragged tile: whole warps stay converged (lanes past the end re-read the last group, report no hit)
     {
@@ -389,10 +406,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
         {
             const uint64_t g = g0 + (uint64_t)u * THREADS + threadIdx.x;
             const uint64_t gc = g < A.group_end ? g : A.group_end - 1;
-            const uint4 v = __ldcs(t4 + gc);
-            uint32_t hit = filter(t4 + gc, v);
+            const uint4 vv = __ldcs(t4 + gc);
+            uint32_t hit = filter(vv, load_next(t4 + gc));
             if (S == 2 && g + 1 == A.group_end && lane != 31) // the neighbour lane holds a clamped group: use the true next word
-                hit = ac_pair_filter<FOLD, false>(s_mem, v, __ldg(reinterpret_cast<const uint32_t *>(t4 + gc + 1)), fold, m1, m2, m3, nbytes);
+                hit = ac_pair_filter<FOLD, false>(s_mem, vv, __ldg(reinterpret_cast<const uint32_t *>(t4 + gc + 1)), fold, m1, m2, m3, nbytes);
             park(g < A.group_end ? hit : 0u, g);
         }
     }
