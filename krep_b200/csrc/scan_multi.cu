@@ -136,6 +136,33 @@ __device__ __forceinline__ unsigned ac_probe(const AcDev &A, uint64_t a, uint32_
     }
 }
 
+// Ordered streaming loads for the software pipeline.  The hardware tracks outstanding loads with a handful of
+// counting scoreboards, so waiting for batch i also waits for every load issued before the wait.  The loop
+// therefore (1) touches batch i (forcing its wait), THEN (2) issues batch i+1, then (3) filters batch i;
+// volatile asm keeps that order.
+__device__ __forceinline__ uint4 ld_stream_ordered(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_u32_ordered(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ld_u64_ordered(const uint2 *p)
+{
+    uint2 v;
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void touch(const uint4 &v, const uint2 &n)
+{
+    asm volatile("" ::"r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(n.x), "r"(n.y));
+}
+
 __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
 {
     uint32_t v;
@@ -321,9 +348,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
     // is issued together with the vector (prefetched), never in front of its use.
     auto load_next = [&](const uint4 *q) -> uint2 {
         if constexpr (S == 2)
-            return lane == 31 ? make_uint2(__ldg(reinterpret_cast<const uint32_t *>(q + 1)), 0u) : make_uint2(0u, 0u);
+            return lane == 31 ? make_uint2(ld_u32_ordered(reinterpret_cast<const uint32_t *>(q + 1)), 0u) : make_uint2(0u, 0u);
         else
-            return __ldg(reinterpret_cast<const uint2 *>(q + 1)); // in bounds by group_end
+            return ld_u64_ordered(reinterpret_cast<const uint2 *>(q + 1)); // in bounds by group_end
     };
     auto filter = [&](const uint4 &v, const uint2 &nx) -> uint32_t {
         if constexpr (S == 2)
@@ -371,7 +398,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
         for (int u = 0; u < UNROLL; u++)
         {
             const uint4 *q = t4 + g0 + (uint64_t)u * THREADS + threadIdx.x;
-            v[u] = __ldcs(q);
+            v[u] = ld_stream_ordered(q);
             nx[u] = load_next(q);
         }
     }
@@ -380,13 +407,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
         uint4 vn[UNROLL];
         uint2 nxn[UNROLL];
         const uint64_t gn = g0 + stride;
-        if (gn + tile <= A.group_end)
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) touch(v[u], nx[u]); // batch i has landed ...
+        if (gn + tile <= A.group_end)                          // ... now put batch i+1 in flight
         {
 #pragma unroll
             for (int u = 0; u < UNROLL; u++)
             {
                 const uint4 *q = t4 + gn + (uint64_t)u * THREADS + threadIdx.x;
-                vn[u] = __ldcs(q);
+                vn[u] = ld_stream_ordered(q);
                 nxn[u] = load_next(q);
             }
         }
