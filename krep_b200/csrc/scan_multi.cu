@@ -66,6 +66,7 @@ struct AcDev
     uint64_t cap;
     unsigned long long *counter;
     uint32_t whole_word, want_positions;
+    uint32_t zero; // always 0; opaque to the compiler (see the software pipeline in k_ac_scan)
 };
 
 static constexpr uint32_t HC1 = 0x9E3779B1u, HC2 = 0x85EBCA77u;
@@ -407,14 +408,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
         uint4 vn[UNROLL];
         uint2 nxn[UNROLL];
         const uint64_t gn = g0 + stride;
+        // batch i has landed: fold one word of every in-flight load into an always-zero value that the next
+        // batch's addresses depend on, so the hardware must wait for batch i before batch i+1 is issued
+        uint32_t landed = 0;
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) touch(v[u], nx[u]); // batch i has landed ...
-        if (gn + tile <= A.group_end)                          // ... now put batch i+1 in flight
+        for (int u = 0; u < UNROLL; u++) landed |= v[u].x | nx[u].x;
+        landed &= A.zero;
+        if (gn + tile <= A.group_end) // ... now put batch i+1 in flight
         {
 #pragma unroll
             for (int u = 0; u < UNROLL; u++)
             {
-                const uint4 *q = t4 + gn + (uint64_t)u * THREADS + threadIdx.x;
+                const uint4 *q = t4 + gn + (uint64_t)u * THREADS + threadIdx.x + landed;
                 vn[u] = ld_stream_ordered(q);
                 nxn[u] = load_next(q);
             }
