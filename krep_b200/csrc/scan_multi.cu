@@ -390,36 +390,47 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
 
     // Register double buffering: the vectors of the next tile are requested before the current tile is
     // filtered, so HBM latency overlaps this warp's own ~260 filter instructions (plus the other warps).
+    // Software pipeline over register double buffers.  The hardware tracks outstanding loads with a handful
+    // of counting scoreboards, so a wait for batch i also waits for anything issued before the wait; the loop
+    // therefore first moves batch i out of the landing registers (that is where the wait happens, on every
+    // path), only then issues batch i+1, and then filters batch i out of the copies.
     uint64_t g0 = A.group_begin + (uint64_t)blockIdx.x * tile;
-    uint4 v[UNROLL];
-    uint2 nx[UNROLL];
+    uint4 vn[UNROLL];
+    uint2 nxn[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++)
+    {
+        vn[u] = make_uint4(0u, 0u, 0u, 0u);
+        nxn[u] = make_uint2(0u, 0u);
+    }
     if (g0 + tile <= A.group_end)
     {
 #pragma unroll
         for (int u = 0; u < UNROLL; u++)
         {
             const uint4 *q = t4 + g0 + (uint64_t)u * THREADS + threadIdx.x;
-            v[u] = ld_stream_ordered(q);
-            nx[u] = load_next(q);
+            vn[u] = ld_stream_ordered(q);
+            nxn[u] = load_next(q);
         }
     }
     for (; g0 + tile <= A.group_end; g0 += stride)
     {
-        uint4 vn[UNROLL];
-        uint2 nxn[UNROLL];
-        const uint64_t gn = g0 + stride;
-        // batch i has landed: fold one word of every in-flight load into an always-zero value that the next
-        // batch's addresses depend on, so the hardware must wait for batch i before batch i+1 is issued
-        uint32_t landed = 0;
+        uint4 v[UNROLL];
+        uint2 nx[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) landed |= v[u].x | nx[u].x;
-        landed &= A.zero;
-        if (gn + tile <= A.group_end) // ... now put batch i+1 in flight
+        for (int u = 0; u < UNROLL; u++)
+        {
+            v[u] = vn[u];
+            nx[u] = nxn[u];
+            touch(v[u], nx[u]);
+        }
+        const uint64_t gn = g0 + stride;
+        if (gn + tile <= A.group_end)
         {
 #pragma unroll
             for (int u = 0; u < UNROLL; u++)
             {
-                const uint4 *q = t4 + gn + (uint64_t)u * THREADS + threadIdx.x + landed;
+                const uint4 *q = t4 + gn + (uint64_t)u * THREADS + threadIdx.x;
                 vn[u] = ld_stream_ordered(q);
                 nxn[u] = load_next(q);
             }
@@ -427,12 +438,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) park(filter(v[u], nx[u]), g0 + (uint64_t)u * THREADS + threadIdx.x);
         drain(false);
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++)
-        {
-            v[u] = vn[u];
-            nx[u] = nxn[u];
-        }
     }
     if (g0 < A.group_end) // ragged tile: whole warps stay converged (lanes past the end re-read the last group, report no hit)
     {
