@@ -271,7 +271,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from krep_b200 import lib
+    from krep_b200 import lib, sharding
     from krep_b200.abi import ALGO_AC, ALGO_AVX2, DeviceResult, Params, Shard
 
     torch.cuda.set_device(local_rank)
@@ -286,8 +286,8 @@ def main():
     maxlen = max(map(len, pats)) if pats else len(wl["needle"])
     halo = maxlen + 1
     last = rank == world - 1
-    g0 = rank * n
-    avail = n if last else n + halo
+    g0, own_len, avail = sharding.shard_bounds(world * n, world, rank, halo)   # weak scaling: n owned bytes per GPU
+    assert own_len == n
     spec = lib.make_spec(SEED, PLANT_SEED, wl["period"], wl["needle"], wl["flags"])
     text = torch.empty(avail + 64, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream()
@@ -316,19 +316,12 @@ def main():
             res.contents.count = 0
             total = L.krep_b200_collect(plan, params.ref(), C.byref(dev), res)
             return total, kms
-        # N>1: one gather of per-GPU counts, then of the (padded) sorted key lists, to rank 0
-        cnt = torch.tensor([dev.stored], dtype=torch.int64, device="cuda")
-        counts = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(counts, cnt)
-        counts = [int(c.item()) for c in counts]
-        mx = max(max(counts), 1)
-        mine = torch.zeros(mx, dtype=torch.int64, device="cuda")
-        L.krep_b200_export_keys(C.byref(dev), mine.data_ptr(), mx, sptr)
-        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-        dist.gather(mine, gathered, dst=0)
+        # N>1: one gather of per-GPU counts, then of the (padded) sorted key lists, to rank 0 (krep_b200/sharding.py)
+        mine = torch.empty(max(int(dev.stored), 1), dtype=torch.int64, device="cuda")
+        L.krep_b200_export_keys(C.byref(dev), mine.data_ptr(), int(dev.stored), sptr)
+        keys, counts = sharding.gather_keys(mine[: int(dev.stored)], world, rank, "cuda")
         total = 0
         if rank == 0:
-            keys = torch.cat([g[:c] for g, c in zip(gathered, counts)]).cpu()
             res.contents.count = 0
             arr = C.cast(keys.data_ptr(), C.POINTER(C.c_uint64))
             total = L.krep_b200_replay(algo, params.ref(), False, arr, keys.numel(), None, 0, res)

@@ -41,7 +41,7 @@ struct AcDevTables
     uint32_t *d_list = nullptr;   // (pattern << 2) | d
     uint8_t *d_pool_val = nullptr, *d_pool_mask = nullptr;
     uint32_t *d_pat_off = nullptr, *d_pat_len = nullptr;
-    uint32_t B = 0, nslots = 0, w = 0, s = 0, npat = 0;
+    uint32_t bitmap_bytes = 0, nslots = 0, w = 0, s = 0, npat = 0;
     uint64_t wmask = 0; // low w bytes
     uint32_t fold = 0xFFFFFFFFu;
     uint32_t mul_lo = 0, mul_hi = 0, mul_b = 0, bit_shift = 0;
@@ -54,7 +54,7 @@ struct AcDev
     const uint32_t *list;
     const uint8_t *pool_val, *pool_mask;
     const uint32_t *pat_off, *pat_len;
-    uint32_t B, nslots, w, npat, bitmap_bytes;
+    uint32_t nslots, w, npat, bitmap_bytes;
     uint32_t wmask_lo, wmask_hi, fold;
     uint32_t mul_lo, mul_hi, mul_b, bit_shift; // hash multipliers (low zero bytes mask the window), bit-index shift for w < 4
     // launch
@@ -435,8 +435,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
                 nxn[u] = load_next(q);
             }
         }
+        uint32_t hit[UNROLL], anyhit = 0;
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) park(filter(v[u], nx[u]), g0 + (uint64_t)u * THREADS + threadIdx.x);
+        for (int u = 0; u < UNROLL; u++) anyhit |= hit[u] = filter(v[u], nx[u]);
+        if (anyhit) // one branch for the whole batch: the common case parks nothing
+        {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) park(hit[u], g0 + (uint64_t)u * THREADS + threadIdx.x);
+        }
         drain(false);
     }
     if (g0 < A.group_end) // ragged tile: whole warps stay converged (lanes past the end re-read the last group, report no hit)
@@ -555,11 +561,13 @@ int ac_build_tables(Plan *plan)
     size_t distinct = 0;
     for (size_t i = 0; i < ents.size(); i++)
         if (i == 0 || ents[i].key != ents[i - 1].key) distinct++;
-    // bitmap size: keep the false-positive rate of one lookup around 0.2 % or better, 16 KB .. 128 KB
-    uint32_t B = 17;
-    while (B < 20 && (double)distinct / (double)(1u << B) > 0.002) B++;
-    T->B = B;
-    std::vector<uint32_t> bitmap(1u << (B - 5), 0);
+    // bitmap size (bytes, any multiple of 16 — addresses come from mulhi, not masking): keep the false-positive
+    // rate of one lookup around 0.2 % or better, 16 KB .. 192 KB of the SM's 227 KB shared memory
+    uint32_t nby = 16u << 10;
+    while (nby < (128u << 10) && (double)distinct / (double)(nby * 8.0) > 0.002) nby *= 2;
+    if (nby == (128u << 10) && (double)distinct / (double)(nby * 8.0) > 0.0015) nby = 192u << 10;
+    T->bitmap_bytes = nby;
+    std::vector<uint32_t> bitmap(nby / 4, 0);
     uint32_t nslots = 16;
     while (nslots < 8 * distinct + 1) nslots *= 2; // load factor <= 1/8: a miss (the common case) ends after ~1.1 probes
     T->nslots = nslots;
@@ -575,7 +583,6 @@ int ac_build_tables(Plan *plan)
             // window bytes c0..c(w-1) as a 64-bit little-endian value
             const uint64_t c = ents[i].key;
             const uint32_t tl = w - 2, tmask = tl >= 4 ? 0xFFFFFFFFu : ((1u << (8 * tl)) - 1);
-            const uint32_t nby = 1u << (B - 3);
             auto word_of = [&](uint32_t t) { return (uint32_t)(((uint64_t)(t * T->mul_lo) * nby) >> 32) >> 2; };
             auto top4 = [](uint32_t x) { return (uint32_t)(((uint64_t)x * 16u) >> 32); };
             const uint32_t first2 = (uint32_t)(c & 0xFFFF), lastT = (uint32_t)(c >> 16) & tmask;
@@ -586,7 +593,7 @@ int ac_build_tables(Plan *plan)
         else
         {
             const uint32_t hsh = lo * T->mul_lo + hi * T->mul_hi;
-            const uint32_t baddr = (uint32_t)(((uint64_t)hsh * (1u << (B - 3))) >> 32); // byte address in the bitmap
+            const uint32_t baddr = (uint32_t)(((uint64_t)hsh * nby) >> 32); // byte address in the bitmap
             const uint32_t bit = (s == 1 ? (hsh >> T->bit_shift) : hsh) & 7;
             bitmap[baddr >> 2] |= 1u << (8 * (baddr & 3) + bit);
         }
@@ -615,7 +622,7 @@ int ac_build_tables(Plan *plan)
         CKB(cudaMemcpy(T->d_pat_len, len.data(), K * 4, cudaMemcpyHostToDevice));
     }
     char name[96];
-    snprintf(name, sizeof name, "window%u/stride%u bitmap2^%u%s", w, s, B, plan->case_sensitive ? "" : " fold");
+    snprintf(name, sizeof name, "window%u/stride%u%s bitmap %uKB%s", w, s, s == 2 ? " paired" : "", nby >> 10, plan->case_sensitive ? "" : " fold");
     plan->filter_name = name;
     return 0;
 }
@@ -647,8 +654,7 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     A.pool_mask = T->d_pool_mask;
     A.pat_off = T->d_pat_off;
     A.pat_len = T->d_pat_len;
-    A.B = T->B;
-    A.bitmap_bytes = 1u << (T->B - 3);
+    A.bitmap_bytes = T->bitmap_bytes;
     A.nslots = T->nslots;
     A.w = T->w;
     A.npat = T->npat;
@@ -681,7 +687,7 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
 
     constexpr int THREADS = 640, UNROLL = 4;
     static int sm_count = 0;
-    const size_t smem = ((size_t)1 << (T->B - 3)) + 128 + (size_t)(THREADS / 32) * AcQueue<UNROLL>::CAP * sizeof(uint64_t);
+    const size_t smem = (size_t)T->bitmap_bytes + 128 + (size_t)(THREADS / 32) * AcQueue<UNROLL>::CAP * sizeof(uint64_t);
     auto kernel = [&]() -> void (*)(AcDev) {
         const bool f = T->fold != 0xFFFFFFFFu;
         if (T->s == 1) return f ? k_ac_scan<1, true, THREADS, UNROLL> : k_ac_scan<1, false, THREADS, UNROLL>;

@@ -1,0 +1,42 @@
+"""Multi-GPU plumbing for the scan path: shard geometry and the single gather of counts/offsets.
+
+This is the analogue of krep's chunker + merge (krep.c:2816-2905, 2928-3004) with two differences that make
+the result equal to the reference's single-chunk run instead of its multi-thread artefacts:
+a match belongs to the shard that contains its START, and -w context bytes come from the neighbouring shards.
+Works on any torch.distributed backend (nccl on the GPUs, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(total_len, world, rank, halo, align=16):
+    """-> (begin, own_len, avail_len): the shard owns [begin, begin+own_len) and can read avail_len bytes from begin.
+
+    own ranges tile [0, total_len) exactly; every shard but the last reads `halo` bytes past its owned range
+    (longest pattern + 1, so an occurrence starting on the last owned byte and the byte after it are visible)."""
+    per = -(-total_len // world)
+    per = -(-per // align) * align
+    begin = min(rank * per, total_len)
+    end = min(begin + per, total_len)
+    avail_end = min(end + halo, total_len)
+    return begin, end - begin, avail_end - begin
+
+
+def gather_keys(local_keys, world, rank, device):
+    """One all_gather of per-rank counts + one gather of the (padded) sorted key lists to rank 0.
+
+    local_keys: 1-D int64 tensor on `device` (sorted, global offsets).  Returns the concatenated, globally
+    ascending key tensor on rank 0 (CPU), None elsewhere, plus the list of per-rank counts."""
+    cnt = torch.tensor([local_keys.numel()], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    counts = [int(c.item()) for c in counts]
+    mx = max(max(counts), 1)
+    mine = torch.zeros(mx, dtype=torch.int64, device=device)
+    mine[: local_keys.numel()] = local_keys
+    gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, gathered, dst=0)
+    if rank != 0:
+        return None, counts
+    # shards are disjoint and ordered by rank, so concatenation in rank order is globally sorted
+    return torch.cat([g[:c] for g, c in zip(gathered, counts)]).cpu(), counts
