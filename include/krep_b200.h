@@ -187,12 +187,14 @@ typedef struct
    uint64_t stored;         /* entries actually stored = min(count, capacity)           */
    const uint64_t *d_keys;  /* device: literal: start offset (global); AC: packed key   */
    int overflow;            /* 1 if count > capacity: call again with a larger capacity */
+   uint64_t text_len;       /* global_offset + avail_len of the scanned shard: the length of the whole text when
+                               the shard is the last (or only) one — what the window kernels' tail logic needs */
 } krep_b200_device_result_t;
 
 /* Scan one shard on `stream` (cudaStream_t, NULL = engine stream): launches the
  * filter+verify kernel and sorts the occurrence list on the device. For a
- * literal plan every key is the global start offset of one occurrence that
- * passed the plan's -w filter.  For an AC plan every key packs
+ * literal plan every key is (global start offset << 3 | tag bits) of one occurrence
+ * that passed the plan's -w filter (tags: see csrc/common.h).  For an AC plan every key packs
  * (end_offset << 24 | (1023 - (len-1)) << 10 ... see krep_b200_ac_key_* below) so
  * that ascending key order is aho_corasick_search's emission order.
  * `want_positions` = 0 counts only (no list is written).
@@ -223,7 +225,9 @@ uint64_t krep_b200_collect(const krep_b200_plan_t *plan, const search_params_t *
  * krep_b200_collect does after reading the device list back).  A multi-GPU host gathers the
  * per-shard lists (already globally ordered across ranks), concatenates them and calls
  * this once, which is the analogue of the reference's merge step (krep.c:2928-3004) without its
- * chunk-edge artefacts.  `text`/`text_len` may be NULL/0 unless params->count_lines_mode is set.
+ * chunk-edge artefacts.  `text` may be NULL unless params->count_lines_mode is set; `text_len` (the length of the
+ * whole text) may be 0 = unknown, except for the AVX2 / AVX-512 window kernels with needles > 16 bytes, whose tail
+ * handling (krep.c:5059, 5260) depends on it.
  * `algo` is a KREP_B200_ALGO_* value; `only_matching` is the -o global to emulate. */
 uint64_t krep_b200_replay(int algo, const search_params_t *params, bool only_matching,
                           const uint64_t *keys, uint64_t nkeys,

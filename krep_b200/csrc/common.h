@@ -12,14 +12,17 @@ namespace kb {
 // ---------------------------------------------------------------------------------------------
 // Occurrence keys.  Every occurrence the device reports is one 64-bit key; ascending key order is
 // the order the emulated reference kernel would have produced.
-//   literal plans : key = (global_start << 2) | (full << 1) | ww_ok
+//   literal plans : key = (global_start << 3) | (full << 2) | (ws_ok << 1) | we_ok
 //                   full  = all pattern_len bytes match (always 1 unless the plan emits prefix hits,
 //                           which only memchr_short_search's -o walk needs, krep.c:4495)
-//                   ww_ok = is_whole_word_match(start, start+len)  (krep.h:312) — 1 when -w is off
+//                   ws_ok / we_ok = the two halves of is_whole_word_match(start, start+len) (krep.h:312):
+//                           no word character before the start / after the end — both 1 when -w is off.
+//                           Kept apart because the tail sub-search of simd_avx2_search / simd_avx512_search
+//                           (krep.c:5068, 5268) cannot see the byte before its sub-buffer.
 //   AC plans      : key = (global_end << 24) | ((1023 - (len-1)) << 14) | pattern_index
 //                   (end ascending, then longest first, then pattern-list order: aho_corasick.c:353-431)
 // ---------------------------------------------------------------------------------------------
-static constexpr int LIT_TAG_BITS = 2;
+static constexpr int LIT_TAG_BITS = 3;
 static constexpr int AC_END_SHIFT = 24;
 static constexpr int AC_LEN_SHIFT = 14;
 static constexpr uint32_t AC_MAX_PATTERNS = 1u << 14;

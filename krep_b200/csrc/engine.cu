@@ -234,6 +234,8 @@ Plan *plan_build(const search_params_t *P, int algo, bool only_matching)
         // Kernels whose cursor also moves past a -w reject (kmp krep.c:1686, sse4.2 krep.c:4839-4848) need the
         // rejected occurrences in the list — but only if occurrences can overlap at all.  Prefix plans always tag.
         bool tag = pl->emit_len != pl->m;
+        // the window kernels' tail sub-search re-evaluates -w against its sub-buffer (krep.c:5068): needs both halves
+        if (algo == KREP_B200_ALGO_AVX2 || algo == KREP_B200_ALGO_AVX512) tag = true;
         if (!tag && !pl->border_free)
             tag = algo == KREP_B200_ALGO_KMP || (algo == KREP_B200_ALGO_SSE42 && !only_matching);
         pl->whole_word = tag ? 2 : 1;
@@ -540,6 +542,7 @@ int krep_b200_scan_shard(const krep_b200_plan_t *plan, const krep_b200_shard_t *
     out->stored = so.stored;
     out->d_keys = so.d_keys;
     out->overflow = so.overflow;
+    out->text_len = shard->global_offset + shard->avail_len;
     return rc;
 }
 

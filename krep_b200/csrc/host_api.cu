@@ -312,6 +312,8 @@ static bool keeps_all(int algo, bool only_matching, const search_params_t *P, co
 {
     if (pl->is_ac) return true;
     if (pl->emit_len != pl->m) return false;
+    // window kernels: tail sub-search, AVX-512's skipped windows and the -m re-basing all need the list
+    if (algo == KREP_B200_ALGO_AVX2 || algo == KREP_B200_ALGO_AVX512) return false;
     if (pl->border_free) return true; // occurrences cannot overlap: every overlap policy keeps all
     switch (algo)
     {
@@ -576,7 +578,7 @@ uint64_t krep_b200_replay(int algo, const search_params_t *P, bool only_matching
         set_error(-3, "krep_b200_replay: -c line counting needs the host text");
         return 0;
     }
-    Replay r{keys, (size_t)nkeys, text, text ? text_len : (SIZE_MAX >> 1), 0};
+    Replay r{keys, (size_t)nkeys, text, text_len ? text_len : (SIZE_MAX >> 1), 0};
     if (algo == KREP_B200_ALGO_AC) return replay_ac(P, r, result);
     algo = resolve_algo(P, algo);
     const uint32_t m = algo == KREP_B200_ALGO_MEMCHR ? 1u : (uint32_t)P->pattern_len;
@@ -603,7 +605,7 @@ uint64_t krep_b200_collect(const krep_b200_plan_t *plan_, const search_params_t 
     const uint64_t *keys = nullptr;
     if (so.stored && fetch_keys(so, &keys) != 0) return 0;
     if (!so.stored) return limited_count(plan->algo, P, plan->is_ac || keeps_all(plan->algo, g_only_matching, P, plan) ? so.count : 0);
-    Replay r{keys, (size_t)so.stored, nullptr, SIZE_MAX >> 1, 0};
+    Replay r{keys, (size_t)so.stored, nullptr, dev->text_len ? (size_t)dev->text_len : (SIZE_MAX >> 1), 0};
     if (plan->is_ac) return replay_ac(P, r, result);
     return replay_literal(plan->algo, P, plan->built_only_matching, plan->m, r, result);
 }

@@ -55,19 +55,19 @@ __device__ __noinline__ unsigned verify_emit(const LitDevParams &p, long long ca
             for (uint32_t k = p.emit_len; k < p.m; k++)
                 if ((t[k] & msk[k]) != val[k]) { full = 0; break; }
     }
-    unsigned ww_ok = 1;
+    unsigned ww_tag = 3; // ws_ok << 1 | we_ok
     if (p.whole_word)
     {
         const uint64_t e = c + p.m;
         const int pb = c > 0 ? (int)t[-1] : p.prev_byte;
         const int nb = e < p.avail_len ? (int)p.text[e] : p.next_byte;
-        ww_ok = !(dev_is_word(pb) || dev_is_word(nb));
-        if (p.whole_word == 1 && !ww_ok) return 0;
+        ww_tag = (dev_is_word(pb) ? 0u : 2u) | (dev_is_word(nb) ? 0u : 1u);
+        if (p.whole_word == 1 && ww_tag != 3) return 0;
     }
     if (p.want_positions)
     {
         const unsigned long long slot = atomicAdd(p.counter, 1ULL);
-        if (slot < p.cap) p.out[slot] = ((p.global_offset + c) << LIT_TAG_BITS) | (full << 1) | ww_ok;
+        if (slot < p.cap) p.out[slot] = ((p.global_offset + c) << LIT_TAG_BITS) | (full << 2) | ww_tag;
         return 0;
     }
     return 1;

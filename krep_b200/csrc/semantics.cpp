@@ -55,9 +55,14 @@ struct Cursor
     const uint64_t *k;
     size_t n, i = 0;
     uint64_t base;
+    bool tail = false; // sub-buffer replay: an occurrence at position 0 has no byte before it (krep.h:314)
     size_t pos(size_t j) const { return (size_t)((k[j] >> LIT_TAG_BITS) - base); }
-    bool full(size_t j) const { return (k[j] >> 1) & 1; }
-    bool ww(size_t j) const { return k[j] & 1; }
+    bool full(size_t j) const { return (k[j] >> 2) & 1; }
+    bool ww(size_t j) const { return (tail && pos(j) == 0) ? (k[j] & 1) : ((k[j] & 3) == 3); }
+    void skip_below_base()
+    {
+        while (i < n && (k[i] >> LIT_TAG_BITS) < base) i++;
+    }
     // index of the first full occurrence starting at or after `from`, or n
     size_t next_full(size_t from)
     {
@@ -296,12 +301,111 @@ static uint64_t replay_sse42(const search_params_t *P, bool only_matching, size_
     return cnt;
 }
 
+// simd_avx2_search for 17..32-byte needles (W = 32, krep.c:4897-5098) and simd_avx512_search for 33..64-byte
+// needles (W = 64, krep.c:5128-5285): W-byte windows from a cursor, every occurrence inside a window kept in
+// ascending order (overlaps included, whatever -o says); -c re-aims the cursor at the next line; the < W tail is a
+// boyer_moore_search on the SUB-buffer (its own -w / -c context, -o advance, re-based -m) whose positions are then
+// re-based by index arithmetic on the result vector; AVX-512 skips a window when < (m-1)+64 bytes remain (krep.c:5171).
+static uint64_t replay_window(const search_params_t *P, bool only_matching, size_t m, size_t W, Cursor c, const char *t,
+                              size_t n, match_result_t *res)
+{
+    if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
+    const size_t maxc = P->max_count;
+    uint64_t cnt = 0;
+    size_t last_line = SIZE_MAX, cur = 0;
+    bool exhausted = false;
+    while (n - cur >= W)
+    {
+        size_t j = c.next_full(cur);
+        if (j == c.n) { exhausted = true; break; }
+        const size_t s0 = c.pos(j);
+        if (s0 - cur >= W)
+        {
+            // empty windows: step as the reference would, but never past the last full window
+            const size_t k0 = (s0 - cur) / W, kmax = (n - cur) / W;
+            cur += W * (k0 < kmax ? k0 : kmax);
+            continue;
+        }
+        if (W == 64 && n - cur < (m - 1) + 64) { cur += 64; continue; }
+        bool line_skipped = false;
+        for (; j < c.n && c.pos(j) < cur + W; j++)
+        {
+            if (!c.full(j)) continue;
+            const size_t s = c.pos(j);
+            if (P->whole_word && !c.ww(j)) continue;
+            bool bumped = false;
+            if (P->count_lines_mode)
+            {
+                const size_t ls = line_start(t, n, s);
+                if (ls != last_line)
+                {
+                    cnt++; last_line = ls; bumped = true;
+                    if (cnt >= maxc) return cnt;
+                    const size_t le = line_end(t, n, ls);
+                    const size_t nx = le < n ? le + 1 : n;
+                    if (nx > cur)
+                    {
+                        cur = nx; // advance is clipped to the remaining length, i.e. cur <= n (nx <= n already)
+                        line_skipped = true;
+                        break;
+                    }
+                }
+            }
+            else
+            {
+                cnt++; bumped = true;
+                if (P->track_positions && res && cnt <= maxc) result_push(res, s, s + m);
+            }
+            if (bumped && cnt >= maxc) return cnt;
+        }
+        if (line_skipped) continue;
+        cur += W;
+    }
+    const size_t rem = n - cur;
+    if (!exhausted && rem >= m)
+    {
+        search_params_t tail = *P;
+        if (maxc != SIZE_MAX) tail.max_count = cnt >= maxc ? 0 : maxc - cnt;
+        Cursor tc = c;
+        tc.base = c.base + cur;
+        tc.tail = true;
+        tc.skip_below_base();
+        const uint64_t tcnt = replay_bmh(&tail, only_matching, m, tc, t ? t + cur : nullptr, rem, res);
+        if (res && P->track_positions && tcnt > 0)
+        {
+            if (W == 32)
+            {
+                const uint64_t b0 = cnt > res->count ? res->count : cnt; // krep.c:5077-5079
+                for (uint64_t k = b0; k < res->count; k++)
+                {
+                    res->positions[k].start_offset += cur;
+                    res->positions[k].end_offset += cur;
+                }
+            }
+            else
+            {
+                const uint64_t b0 = res->count >= tcnt ? res->count - tcnt : 0; // krep.c:5275
+                for (uint64_t k = 0; k < tcnt && b0 + k < res->count; k++)
+                {
+                    res->positions[b0 + k].start_offset += cur;
+                    res->positions[b0 + k].end_offset += cur;
+                }
+            }
+        }
+        cnt += tcnt;
+        if (W == 32 && maxc != SIZE_MAX && cnt > maxc) cnt = maxc; // krep.c:5092
+    }
+    return cnt;
+}
+
 uint64_t replay_literal(int algo, const search_params_t *P, bool only_matching, uint32_t m, const Replay &r,
                         match_result_t *res)
 {
     Cursor c{r.keys, r.n, 0, r.base};
     switch (algo)
     {
+    case KREP_B200_ALGO_AVX2: return replay_window(P, only_matching, m, 32, c, r.text, r.text_len, res);   // resolved: 17..32 B
+    case KREP_B200_ALGO_AVX512: return replay_window(P, only_matching, m, 64, c, r.text, r.text_len, res); // resolved: 33..64 B
     case KREP_B200_ALGO_KMP: return replay_kmp(P, m, c, r.text, r.text_len, res);
     case KREP_B200_ALGO_MEMCHR: return replay_memchr(P, c, r.text, r.text_len, res);
     case KREP_B200_ALGO_MEMCHR_SHORT: return replay_memchr_short(P, only_matching, m, c, r.text, r.text_len, res);

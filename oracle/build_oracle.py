@@ -4,6 +4,7 @@
   _ref/libkrep_ref.so     <- /root/reference/{krep.c,aho_corasick.c} compiled where they lie,
                              through oracle/ref_wrap.c (adds accessors for krep.c's static flags)
   _ref/krep               <- the stock reference CLI, same sources, with its own main()
+  _ref/libkrep_ref512.so  <- the same library as its AVX-512 build (adds simd_avx512_search)
 
 The reference's own Makefile is NOT run; its flag set (Makefile:9-41) is restated here:
 -O3 -std=c11 -pthread -D_GNU_SOURCE -D_DEFAULT_SOURCE -funroll-loops, SIMD flags fixed to
@@ -70,6 +71,22 @@ def build_ref(force=False):
     return lib, cli
 
 
+def build_ref512(force=False):
+    """The AVX-512 build of the reference library (Makefile:34-35 flag set) — the only build in which
+    simd_avx512_search exists.  Used by tests to pin oracle_avx512_search; never loaded on a CPU without AVX-512BW."""
+    lib = os.path.join(OUT_REF, "libkrep_ref512.so")
+    if not ref_available():
+        return lib if os.path.exists(lib) else None
+    os.makedirs(OUT_REF, exist_ok=True)
+    srcs = [os.path.join(REF_DIR, f) for f in ("krep.c", "aho_corasick.c", "krep.h", "aho_corasick.h")]
+    wrap = os.path.join(HERE, "ref_wrap.c")
+    if force or _stale(lib, srcs + [wrap]):
+        _run(["gcc", *CFLAGS, "-mavx512f", "-mavx512bw", "-DTESTING", "-fPIC", "-shared", "-I", REF_DIR, "-o", lib,
+              wrap, os.path.join(REF_DIR, "aho_corasick.c")])
+    return lib
+
+
 if __name__ == "__main__":
     print(build_port(force="--force" in sys.argv))
     print(build_ref(force="--force" in sys.argv))
+    print(build_ref512(force="--force" in sys.argv))

@@ -371,6 +371,124 @@ uint64_t oracle_sse42_search(const search_params_t *P, const char *text, size_t 
 }
 
 /* ==========================================================================
+ * simd_avx2_search (krep.c:4877-5101, 17..32-byte needles) and
+ * simd_avx512_search (krep.c:5108-5286, 33..64-byte needles).
+ * Both walk W-byte windows (W = 32 / 64) from a cursor that starts at 0 and
+ * advances by W — or, in -c mode, jumps to the start of the next line after a
+ * counted line (krep.c:4996-5014 / 5211-5229).  Inside a window EVERY start
+ * whose first and last byte match is memcmp-verified in ascending order, so
+ * occurrences overlap freely whatever -o says.  What is observable beyond that:
+ *   - the tail (< W bytes) is handed to a sub-search on the sub-buffer that
+ *     starts at the cursor: boyer_moore_search for AVX2 (krep.c:5068), and
+ *     simd_avx2_search -> boyer_moore_search (needle > 32) for AVX-512
+ *     (krep.c:5268).  -w and -c are evaluated against the SUB-buffer there
+ *     (no byte before its first byte; line starts clipped to it), -o takes
+ *     BMH's pattern_len advance, and -m is re-based;
+ *   - the tail's positions are re-based by index arithmetic on the result
+ *     vector (krep.c:5072-5088 / 5271-5281), reproduced literally;
+ *   - AVX-512 skips a window unverified when fewer than (m-1)+64 bytes remain
+ *     (krep.c:5171, falls through to 5255) — matches there are lost.
+ * A candidate whose last byte would lie past the buffer compares against the
+ * zero padding of the safe buffer (krep.c:4944-4956): never a hit for needles
+ * that do not end in NUL, which is what is restated here.
+ * ========================================================================== */
+static uint64_t window_search(const search_params_t *P, const char *text, size_t n, match_result_t *res, size_t W)
+{
+    const unsigned char *t = (const unsigned char *)text, *p = (const unsigned char *)P->pattern;
+    const size_t m = P->pattern_len, maxc = P->max_count;
+    uint64_t cnt = 0;
+    size_t last_line = SIZE_MAX, cur = 0, rem = n;
+    while (rem >= W)
+    {
+        bool line_skipped = false;
+        if (W == 64 && rem < (m - 1) + 64) { cur += 64; rem -= 64; continue; } /* krep.c:5171 */
+        for (size_t i = 0; i < W; i++)
+        {
+            const size_t s = cur + i;
+            if (s + m > n || !occurs(t + s, p, m, true)) continue;
+            if (P->whole_word && !whole_word(text, n, s, s + m)) continue;
+            bool bumped = false;
+            if (P->count_lines_mode)
+            {
+                const size_t ls = line_start(text, n, s);
+                if (ls != last_line)
+                {
+                    cnt++; last_line = ls; bumped = true;
+                    if (cnt >= maxc) return cnt;
+                    const size_t le = line_end(text, n, ls);
+                    const size_t nx = le < n ? le + 1 : n;
+                    if (nx > cur)
+                    {
+                        size_t adv = nx - cur;
+                        if (adv > rem) adv = rem;
+                        cur += adv; rem -= adv;
+                        line_skipped = true;
+                        break;
+                    }
+                }
+            }
+            else
+            {
+                cnt++; bumped = true;
+                if (P->track_positions && res && cnt <= maxc) push(res, s, s + m);
+            }
+            if (bumped && cnt >= maxc) return cnt;
+        }
+        if (line_skipped) continue;
+        cur += W; rem -= W;
+    }
+    if (rem >= m)
+    {
+        search_params_t tail = *P;
+        if (maxc != SIZE_MAX) tail.max_count = cnt >= maxc ? 0 : maxc - cnt;
+        const uint64_t tc = oracle_boyer_moore_search(&tail, text + cur, rem, res);
+        if (res && P->track_positions && tc > 0)
+        {
+            if (W == 32)
+            {
+                uint64_t b0 = cnt > res->count ? res->count : cnt; /* krep.c:5077-5079 */
+                for (uint64_t k = b0; k < res->count; k++)
+                {
+                    res->positions[k].start_offset += cur;
+                    res->positions[k].end_offset += cur;
+                }
+            }
+            else
+            {
+                uint64_t b0 = res->count >= tc ? res->count - tc : 0; /* krep.c:5275 */
+                for (uint64_t k = 0; k < tc && b0 + k < res->count; k++)
+                {
+                    res->positions[b0 + k].start_offset += cur;
+                    res->positions[b0 + k].end_offset += cur;
+                }
+            }
+        }
+        cnt += tc;
+        if (W == 32 && maxc != SIZE_MAX && cnt > maxc) cnt = maxc; /* krep.c:5092 */
+    }
+    return cnt;
+}
+
+uint64_t oracle_avx2_search(const search_params_t *P, const char *text, size_t n, match_result_t *res)
+{
+    const size_t m = P->pattern_len;
+    if (m == 0 || m > 32 || !P->case_sensitive || n < m) return oracle_boyer_moore_search(P, text, n, res); /* krep.c:4883 */
+    if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
+    if (m <= 16) return oracle_sse42_search(P, text, n, res); /* krep.c:4892 */
+    return window_search(P, text, n, res, 32);
+}
+
+/* As compiled into an AVX-512 build of the reference (Makefile:34-35). */
+uint64_t oracle_avx512_search(const search_params_t *P, const char *text, size_t n, match_result_t *res)
+{
+    const size_t m = P->pattern_len;
+    if (m == 0 || m > 64 || !P->case_sensitive || n < m) return oracle_avx2_search(P, text, n, res); /* krep.c:5115 */
+    if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
+    if (m <= 32) return oracle_avx2_search(P, text, n, res); /* krep.c:5123 */
+    return window_search(P, text, n, res, 64);
+}
+
+/* ==========================================================================
  * ac_trie_build / aho_corasick_search — aho_corasick.c:111-271, 299-466.
  * Restated with array-indexed nodes.  Emission order: ascending end offset;
  * at one end offset the deepest node first, then along the failure chain;

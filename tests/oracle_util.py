@@ -19,16 +19,19 @@ FUNCS = {
     "memchr_short": ("oracle_memchr_short_search", "memchr_short_search"),
     "sse42": ("oracle_sse42_search", "simd_sse42_search"),
     "aho_corasick": ("oracle_aho_corasick_search", "aho_corasick_search"),
+    "avx2": ("oracle_avx2_search", "simd_avx2_search"),
 }
+# only present in an AVX-512 build of the reference (oracle/_ref/libkrep_ref512.so)
+FUNCS_512 = {"avx512": ("oracle_avx512_search", "simd_avx512_search")}
 
 
 class _Checker:
-    def __init__(self, lib, kind):
+    def __init__(self, lib, kind, funcs=None):
         self.lib = lib
         self.kind = kind  # "port" | "reference"
         idx = 0 if kind == "port" else 1
         self.fn = {}
-        for k, names in FUNCS.items():
+        for k, names in (funcs or FUNCS).items():
             f = getattr(lib, names[idx])
             f.argtypes = _SIG
             f.restype = C.c_uint64
@@ -82,7 +85,7 @@ _cache = {}
 
 def port():
     if "port" not in _cache:
-        _cache["port"] = _Checker(C.CDLL(build_oracle.build_port()), "port")
+        _cache["port"] = _Checker(C.CDLL(build_oracle.build_port()), "port", {**FUNCS, **FUNCS_512})
     return _cache["port"]
 
 
@@ -92,6 +95,22 @@ def reference():
         lib, _ = build_oracle.build_ref()
         _cache["ref"] = _Checker(C.CDLL(lib), "reference") if lib else None
     return _cache["ref"]
+
+
+def reference512():
+    """The reference compiled as its AVX-512 build (simd_avx512_search exists only there), or None when it is not
+    available or this CPU cannot execute AVX-512BW."""
+    if "ref512" not in _cache:
+        lib = build_oracle.build_ref512()
+        ok = False
+        if lib:
+            try:
+                with open("/proc/cpuinfo") as f:
+                    ok = "avx512bw" in f.read()
+            except OSError:
+                ok = False
+        _cache["ref512"] = _Checker(C.CDLL(lib), "reference", {**FUNCS, **FUNCS_512}) if ok else None
+    return _cache["ref512"]
 
 
 def ref_cli():

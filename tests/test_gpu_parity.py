@@ -37,10 +37,10 @@ def test_committed_reference_fixtures_through_c_abi():
         assert cnt == c["count_out"] and [list(x) for x in pos] == c["pos_out"], c
 
 
-@pytest.mark.parametrize("func", list(ou.FUNCS))
+@pytest.mark.parametrize("func", list(ou.FUNCS) + ["avx512"])
 def test_random_differential_vs_oracle(func):
     rng = random.Random(4242 + len(func))
-    chk = checker()
+    chk = (ou.reference512() or ou.port()) if func == "avx512" else checker()
     for _ in range(700):
         pats, text, opts, with_res = random_case(rng, func)
         got = lib.search(func, Params(pats, **opts), text, with_result=with_res)
@@ -61,6 +61,7 @@ def _mixed_text(rng, n):
     ("sse42", b"needle"), ("sse42", b"the quick"), ("sse42", b"abab"), ("boyer_moore", b"aaa"),
     ("boyer_moore", b"needle Brown"), ("kmp", b"abab"), ("memchr", b"x"), ("memchr_short", b"ab"),
     ("boyer_moore", b"the quick Brown fox_1 needle NEEDLE"), ("sse42", b"fox_1 needle NEE"),
+    ("avx2", b"needle Brown fox_1 ne"), ("avx2", b"ab abab aaa x ab abab"), ("avx2", b"the quick Brown fox_1 needle NEE"),
 ])
 @pytest.mark.parametrize("opts", [
     dict(), dict(case_sensitive=False), dict(whole_word=True), dict(count=True), dict(only_matching=True),

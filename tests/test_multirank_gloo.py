@@ -63,10 +63,10 @@ def shard_keys(func, pats, opts, text, begin, own_len, avail_len):
             if 0 <= start < own_len and end <= avail_len:
                 out.append(((end + begin) << 24) | (k & 0xFFFFFF))
         else:
-            start = (k >> 2) - off
+            start = (k >> 3) - off
             m = len(pats[0])
             if 0 <= start < own_len and start + m <= avail_len:
-                out.append(((start + begin) << 2) | (k & 3))
+                out.append(((start + begin) << 3) | (k & 7))
     return out
 
 

@@ -108,8 +108,17 @@ def random_case(rng, func):
         if rng.random() < 0.2:
             pats.append(pats[0])  # duplicate pattern -> duplicate emissions (aho_corasick.c:361)
     else:
-        lo, hi = {"memchr": (1, 1), "memchr_short": (2, 3), "sse42": (1, 18)}.get(func, (1, 20))
+        lo, hi = {"memchr": (1, 1), "memchr_short": (2, 3), "sse42": (1, 18), "avx2": (14, 36),
+                  "avx512": (28, 70)}.get(func, (1, 20))
         m = rng.randint(lo, hi)
+        if func in ("avx2", "avx512") and rng.random() < 0.5:
+            # periodic needle + periodic text: many overlapping occurrences, window / tail edges everywhere
+            unit = bytes(rng.choice(alpha) for _ in range(rng.randint(1, 3)))
+            n = rng.choice([31, 32, 33, 47, 63, 64, 65, 90, 96, 127, 128, 129, 200, 257])
+            text = bytearray((unit * (n // len(unit) + 1))[:n])
+            for _ in range(rng.randint(0, 4)):
+                text[rng.randrange(n)] = rng.choice(b" \n_xZ")
+            text = bytes(text)
         if text and rng.random() < 0.7 and len(text) >= m:
             s = rng.randrange(0, len(text) - m + 1)
             pat = text[s:s + m]
@@ -119,7 +128,7 @@ def random_case(rng, func):
             pat = pat.swapcase()
         pats = [pat]
     opts = dict(
-        case_sensitive=rng.random() < 0.5,
+        case_sensitive=rng.random() < (0.9 if func in ("avx2", "avx512") else 0.5),
         count=rng.random() < 0.35,
         only_matching=rng.random() < 0.4,
         whole_word=rng.random() < 0.35,
@@ -134,9 +143,23 @@ def test_port_vs_compiled_reference_differential(func):
     if ref is None:
         pytest.skip("compiled reference not available")
     rng = random.Random(0xC0FFEE ^ hash(func) & 0xFFFF)
-    rng = random.Random({"boyer_moore": 1, "kmp": 2, "memchr": 3, "memchr_short": 4, "sse42": 5, "aho_corasick": 6}[func])
+    rng = random.Random({"boyer_moore": 1, "kmp": 2, "memchr": 3, "memchr_short": 4, "sse42": 5, "aho_corasick": 6,
+                         "avx2": 7}[func])
     for it in range(3000):
         pats, text, opts, with_res = random_case(rng, func)
         a = ou.port().run(func, Params(pats, **opts), text, with_result=with_res)
         b = ref.run(func, Params(pats, **opts), text, with_result=with_res)
         assert a == b, (func, pats, text, opts, with_res, a, b)
+
+
+def test_port_vs_avx512_build_of_the_reference():
+    """simd_avx512_search only exists in the reference's AVX-512 build; pin oracle_avx512_search against it."""
+    ref = ou.reference512()
+    if ref is None:
+        pytest.skip("AVX-512 build of the reference not available / CPU without AVX-512BW")
+    rng = random.Random(8)
+    for it in range(3000):
+        pats, text, opts, with_res = random_case(rng, "avx512")
+        a = ou.port().run("avx512", Params(pats, **opts), text, with_result=with_res)
+        b = ref.run("avx512", Params(pats, **opts), text, with_result=with_res)
+        assert a == b, (pats, text, opts, with_res, a, b)

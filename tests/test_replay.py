@@ -9,12 +9,12 @@ import pytest
 
 import oracle_util as ou
 from krep_b200 import lib
-from krep_b200.abi import (ALGO_AC, ALGO_BMH, ALGO_KMP, ALGO_MEMCHR, ALGO_MEMCHR_SHORT, ALGO_SSE42, MatchResult, Params,
-                           SIZE_MAX)
+from krep_b200.abi import (ALGO_AC, ALGO_AVX2, ALGO_AVX512, ALGO_BMH, ALGO_KMP, ALGO_MEMCHR, ALGO_MEMCHR_SHORT, ALGO_SSE42,
+                           MatchResult, Params, SIZE_MAX)
 from test_oracle import random_case
 
 ALGO = {"boyer_moore": ALGO_BMH, "kmp": ALGO_KMP, "memchr": ALGO_MEMCHR, "memchr_short": ALGO_MEMCHR_SHORT,
-        "sse42": ALGO_SSE42, "aho_corasick": ALGO_AC}
+        "sse42": ALGO_SSE42, "aho_corasick": ALGO_AC, "avx2": ALGO_AVX2, "avx512": ALGO_AVX512}
 
 
 def lc(b):
@@ -27,6 +27,11 @@ def wordc(c):
 
 def ww_ok(text, s, e):
     return not ((s > 0 and wordc(text[s - 1])) or (e < len(text) and wordc(text[e])))
+
+
+def ww_tag(text, s, e):
+    """ws_ok << 1 | we_ok — the two halves of is_whole_word_match as the device tags them (csrc/common.h)."""
+    return (0 if (s > 0 and wordc(text[s - 1])) else 2) | (0 if (e < len(text) and wordc(text[e])) else 1)
 
 
 def device_like_keys(func, pats, text, cs, whole_word, only_matching):
@@ -58,8 +63,8 @@ def device_like_keys(func, pats, text, cs, whole_word, only_matching):
             if tt[s:s + m] != pp or s + m > len(text):
                 continue
             full = True
-        ok = (not whole_word) or ww_ok(text, s, s + m)
-        keys.append((s << 2) | (int(full) << 1) | int(ok))
+        tag = ww_tag(text, s, s + m) if whole_word else 3
+        keys.append((s << 3) | (int(full) << 2) | tag)
     return keys
 
 
@@ -101,7 +106,10 @@ def early_out(func, params, text):
 @pytest.mark.parametrize("func", list(ALGO))
 def test_replay_matches_oracle(func):
     rng = random.Random(77 + ALGO[func])
-    checkers = [ou.port()] + ([ou.reference()] if ou.reference() else [])
+    if func == "avx512":
+        checkers = [ou.port()] + ([ou.reference512()] if ou.reference512() else [])
+    else:
+        checkers = [ou.port()] + ([ou.reference()] if ou.reference() else [])
     n_checked = 0
     for _ in range(2500):
         pats, text, opts, with_res = random_case(rng, func)
