@@ -48,6 +48,7 @@ struct LitDevParams
     uint32_t K[4];                   // filter constants (already folded)
     uint32_t fold;                   // AND-mask applied to text words before comparing (0xFFFFFFFF or 0xDFDFDFDF)
     uint32_t win_mask;               // WINDOW4: mask of the low min(4, emit_len) bytes
+    uint32_t mulc[3];                // WINDOW4: 2^24, 2^16, 2^8 — window extraction on the FMA pipe (scan_literal.cu)
     const uint8_t *pat_val;          // device: pattern[k] & pat_mask[k]
     const uint8_t *pat_mask;         // device: 0xDF where case folds, else 0xFF
     uint64_t *out;                   // device key buffer (may be null when !want_positions)

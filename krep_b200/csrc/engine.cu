@@ -333,6 +333,9 @@ int launch_scan(const Plan *plan, const krep_b200_shard_t *sh, int want_position
     for (int d = 0; d < 4; d++) p.K[d] = plan->K[d];
     p.fold = plan->fold;
     p.win_mask = plan->win_mask;
+    p.mulc[0] = 1u << 24;
+    p.mulc[1] = 1u << 16;
+    p.mulc[2] = 1u << 8;
     p.pat_val = plan->d_pat_val;
     p.pat_mask = plan->d_pat_mask;
     p.out = E.d_keys[0];

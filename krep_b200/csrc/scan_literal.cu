@@ -160,15 +160,33 @@ __global__ void __launch_bounds__(256, 4) k_lit_aligned4(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------ WINDOW4
-__device__ __forceinline__ bool hit_pair(uint32_t lo, uint32_t hi, uint32_t mask, uint32_t k0)
+// The 4-byte window at byte offset 4k+r is (lo >> 8r) | (hi << (32-8r)).  A funnel shift would put it on the ALU
+// pipe next to the compares, which is what bounds this kernel (SHF/LOP3/ISETP all issue there at half rate).  The
+// same value is umulhi(lo, 2^(32-8r)) + hi * 2^(32-8r) — an IMAD.HI and an IMAD on the otherwise idle FMA pipe —
+// so per text word the ALU pipe only sees the case fold (one LOP3, -i only) and the four compares.  The
+// multipliers come from kernel parameters so that the compiler cannot strength-reduce them back into shifts.
+template <bool MASKED>
+__device__ __forceinline__ bool hit_pair(uint32_t lo, uint32_t hi, uint32_t mask, uint32_t k0, uint32_t c1, uint32_t c2,
+                                         uint32_t c3)
 {
-    return ((lo & mask) == k0) | ((__funnelshift_r(lo, hi, 8) & mask) == k0) |
-           ((__funnelshift_r(lo, hi, 16) & mask) == k0) | ((__funnelshift_r(lo, hi, 24) & mask) == k0);
+    uint32_t x0 = lo, x1 = hi * c1 + __umulhi(lo, c1), x2 = hi * c2 + __umulhi(lo, c2), x3 = hi * c3 + __umulhi(lo, c3);
+    if (MASKED)
+    {
+        x0 &= mask; x1 &= mask; x2 &= mask; x3 &= mask;
+    }
+    return (x0 == k0) | (x1 == k0) | (x2 == k0) | (x3 == k0);
 }
-__device__ __forceinline__ bool hit_vec_w(const uint4 &v, uint32_t nx, uint32_t mask, uint32_t k0)
+template <bool FOLD, bool MASKED>
+__device__ __forceinline__ bool hit_vec_w(const uint4 &v, uint32_t nx, uint32_t fold, uint32_t mask, uint32_t k0,
+                                          uint32_t c1, uint32_t c2, uint32_t c3)
 {
-    return hit_pair(v.x, v.y, mask, k0) | hit_pair(v.y, v.z, mask, k0) | hit_pair(v.z, v.w, mask, k0) |
-           hit_pair(v.w, nx, mask, k0);
+    uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w, w4 = nx;
+    if (FOLD)
+    {
+        w0 &= fold; w1 &= fold; w2 &= fold; w3 &= fold; w4 &= fold;
+    }
+    return hit_pair<MASKED>(w0, w1, mask, k0, c1, c2, c3) | hit_pair<MASKED>(w1, w2, mask, k0, c1, c2, c3) |
+           hit_pair<MASKED>(w2, w3, mask, k0, c1, c2, c3) | hit_pair<MASKED>(w3, w4, mask, k0, c1, c2, c3);
 }
 
 __device__ __noinline__ unsigned slow_window4(const LitDevParams &p, uint64_t group, uint4 v, uint32_t nx)
@@ -187,11 +205,12 @@ __device__ __noinline__ unsigned slow_window4(const LitDevParams &p, uint64_t gr
     return n;
 }
 
-template <int UNROLL>
+template <bool FOLD, bool MASKED, int UNROLL>
 __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ LitDevParams p)
 {
     const uint4 *__restrict__ t4 = reinterpret_cast<const uint4 *>(p.text);
-    const uint32_t mask = p.fold & p.win_mask, k0 = p.K[0];
+    const uint32_t fold = p.fold, mask = p.win_mask, k0 = p.K[0];
+    const uint32_t c1 = p.mulc[0], c2 = p.mulc[1], c3 = p.mulc[2]; // 2^24, 2^16, 2^8
     unsigned long long local_cnt = 0;
     const uint64_t tile = (uint64_t)blockDim.x * UNROLL;
     const uint64_t stride = (uint64_t)gridDim.x * tile;
@@ -207,15 +226,15 @@ __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ 
             v[u] = ld_stream(q);
             nx[u] = __ldg(reinterpret_cast<const uint32_t *>(q + 1)); // first word of the next vector (L1/L2 hit)
         }
-        bool hit = false;
+        uint32_t hm = 0; // bit u: vector u holds a candidate
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) hit |= hit_vec_w(v[u], nx[u], mask, k0);
-        if (hit)
+        for (int u = 0; u < UNROLL; u++)
+            hm |= hit_vec_w<FOLD, MASKED>(v[u], nx[u], fold, mask, k0, c1, c2, c3) ? (1u << u) : 0u;
+        if (hm)
         {
 #pragma unroll
             for (int u = 0; u < UNROLL; u++)
-                if (hit_vec_w(v[u], nx[u], mask, k0))
-                    local_cnt += slow_window4(p, g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u], nx[u]);
+                if ((hm >> u) & 1u) local_cnt += slow_window4(p, g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u], nx[u]);
         }
     }
     if (g0 < p.group_end)
@@ -227,7 +246,7 @@ __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ 
             {
                 const uint4 v = ld_stream(t4 + g);
                 const uint32_t nx = __ldg(reinterpret_cast<const uint32_t *>(t4 + g + 1));
-                if (hit_vec_w(v, nx, mask, k0)) local_cnt += slow_window4(p, g, v, nx);
+                if (hit_vec_w<FOLD, MASKED>(v, nx, fold, mask, k0, c1, c2, c3)) local_cnt += slow_window4(p, g, v, nx);
             }
         }
     }
@@ -236,7 +255,7 @@ __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------ launch
 static int g_sm_count = 0;
-static int g_occ[3] = {0, 0, 0};
+static int g_occ[6] = {0, 0, 0, 0, 0, 0};
 
 template <typename K>
 static int occupancy(K kernel)
@@ -256,17 +275,27 @@ void launch_literal(const Plan *plan, const LitDevParams &p, cudaStream_t s)
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
         g_occ[0] = occupancy(k_lit_aligned4<false, UNROLL>);
         g_occ[1] = occupancy(k_lit_aligned4<true, UNROLL>);
-        g_occ[2] = occupancy(k_lit_window4<UNROLL>);
+        g_occ[2] = occupancy(k_lit_window4<false, false, UNROLL>);
+        g_occ[3] = occupancy(k_lit_window4<true, false, UNROLL>);
+        g_occ[4] = occupancy(k_lit_window4<false, true, UNROLL>);
+        g_occ[5] = occupancy(k_lit_window4<true, true, UNROLL>);
     }
     const uint64_t groups = p.group_end > p.group_begin ? p.group_end - p.group_begin : 0;
     const uint64_t tile = 256ull * UNROLL;
     uint64_t tiles = (groups + tile - 1) / tile;
     if (tiles == 0) tiles = 1; // still need the tail warp
-    const int which = plan->filter == FILTER_WINDOW4 ? 2 : (plan->fold != 0xFFFFFFFFu ? 1 : 0);
+    const bool folded = plan->fold != 0xFFFFFFFFu, masked = plan->win_mask != 0xFFFFFFFFu;
+    const int which = plan->filter == FILTER_WINDOW4 ? 2 + (folded ? 1 : 0) + (masked ? 2 : 0) : (folded ? 1 : 0);
     uint64_t resident = (uint64_t)g_sm_count * g_occ[which];
     const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
     if (which == 2)
-        k_lit_window4<UNROLL><<<grid, 256, 0, s>>>(p);
+        k_lit_window4<false, false, UNROLL><<<grid, 256, 0, s>>>(p);
+    else if (which == 3)
+        k_lit_window4<true, false, UNROLL><<<grid, 256, 0, s>>>(p);
+    else if (which == 4)
+        k_lit_window4<false, true, UNROLL><<<grid, 256, 0, s>>>(p);
+    else if (which == 5)
+        k_lit_window4<true, true, UNROLL><<<grid, 256, 0, s>>>(p);
     else if (which == 1)
         k_lit_aligned4<true, UNROLL><<<grid, 256, 0, s>>>(p);
     else

@@ -45,6 +45,7 @@ struct AcDevTables
     uint64_t wmask = 0; // low w bytes
     uint32_t fold = 0xFFFFFFFFu;
     uint32_t mul_lo = 0, mul_hi = 0, mul_b = 0, bit_shift = 0;
+    bool tri4 = false; // stride-4 trigram filter (Lmin == 6), see k_ac_tri4
 };
 
 struct AcDev
@@ -145,6 +146,12 @@ __device__ __forceinline__ uint4 ld_stream_ordered(const uint4 *p)
 {
     uint4 v;
     asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_vec_ordered(const uint4 *p) // default L2 policy: candidate groups are re-read from L2
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 __device__ __forceinline__ uint32_t ld_u32_ordered(const uint32_t *p)
@@ -478,6 +485,184 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
     }
 }
 
+// =============================================================================================
+// TRI4 — the stride-4 filter for pattern sets whose shortest pattern has exactly 6 bytes.
+//
+// With Lmin = 6 a sampling stride of 4 leaves only a 3-byte window (w + s - 1 <= Lmin), and 4*K trigrams of
+// lowercase-ish patterns are far too dense for a plain bitmap.  But an occurrence at p = a - d (a aligned, d in 0..3)
+// of a pattern of length L also fixes byte a+3 whenever L - d >= 4 — i.e. for every (pattern, d) except (L = 6, d = 3).
+// So one aligned text word w = bytes [a, a+4) is the whole lookup key, with NO shifting and NO neighbour bytes:
+//     word index = hash(low three bytes of w)          IMAD (multiplier with a zero low byte drops byte 3) + IMAD.HI
+//     bit index  = low five bits of byte 3 of w         IMAD.HI by 2^8 (w >> 24 on the FMA pipe); SHF.W wraps at 32
+// and the (L = 6, d = 3) entries, which do not know byte a+3, set all 32 bits of their word.  Per 16 bytes that is
+// 4 lookups of ~7 instructions split evenly between the FMA and ALU pipes, and 4 shared-memory loads — half the
+// instructions of the stride-2 paired filter above.  A lookup passes for ~1 % of the positions of English-like text
+// against 1000 patterns; those groups are queued per warp and verified 32 at a time against the exact table below.
+//
+// Exact table (L2 resident, same AcSlot open addressing): key = the folded word w for entries that know byte a+3,
+// key = (1 << 32) | trigram for those that do not; value = list of (pattern << 2 | d).
+// =============================================================================================
+template <bool FOLD>
+__device__ __forceinline__ uint32_t tri4_filter(uint32_t s_base, const uint4 &v, uint32_t fold, uint32_t m1, uint32_t nbytes,
+                                                uint32_t c8)
+{
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        if (FOLD) w[k] &= fold;
+        const uint32_t addr = __umulhi(w[k] * m1, nbytes) & ~3u;
+        const uint32_t word = lds_u32(s_base + addr);
+        acc |= __funnelshift_r(word, 0u, __umulhi(w[k], c8));
+    }
+    return acc & 1u;
+}
+
+// one candidate group per lane (valid lanes only); every lane walks its own hits, probes and pattern compares
+template <bool FOLD>
+__device__ __noinline__ unsigned tri4_verify_groups(const AcDev &A, uint32_t s_base, uint64_t g, bool valid)
+{
+    unsigned n = 0;
+    if (!valid) return 0;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(A.text) + g);
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        if (FOLD) w[k] &= A.fold;
+        const uint32_t word = lds_u32(s_base + (__umulhi(w[k] * A.mul_lo, A.bitmap_bytes) & ~3u));
+        if (!((word >> ((w[k] >> 24) & 31u)) & 1u)) continue;
+        const uint64_t a = g * 16 + 4 * k;
+        // probe 0: entries that know byte a+3 (key = w); probe 1: entries that do not (key = 1<<32 | trigram)
+        for (int wild = 0; wild < (A.mul_b ? 2 : 1); wild++)
+        {
+            const uint32_t lo = wild ? (w[k] & 0x00FFFFFFu) : w[k], hi = (uint32_t)wild;
+            const uint64_t key = ((uint64_t)hi << 32) | lo;
+            uint32_t h = slot_hash(lo, hi) & (A.nslots - 1);
+            for (;;)
+            {
+                const AcSlot sl = A.slots[h];
+                if (sl.count == 0) break;
+                if (sl.key == key)
+                {
+                    for (uint32_t i = 0; i < sl.count; i++)
+                    {
+                        const uint32_t e = A.list[sl.first + i];
+                        n += ac_verify_emit(A, e >> 2, (long long)a - (long long)(e & 3));
+                    }
+                    break;
+                }
+                h = (h + 1) & (A.nslots - 1);
+            }
+        }
+    }
+    return n;
+}
+
+template <bool FOLD, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ AcDev A)
+{
+    extern __shared__ __align__(16) uint8_t s_mem[];
+    constexpr int QCAP = 64; // < 32 left over + at most 32 new per push
+    const uint32_t nbytes = A.bitmap_bytes;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *s_q = reinterpret_cast<uint64_t *>(s_mem + nbytes) + warp * QCAP;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.bitmap);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_mem);
+        for (uint32_t i = threadIdx.x; i < nbytes / 16; i += THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_mem);
+    const uint4 *__restrict__ t4 = reinterpret_cast<const uint4 *>(A.text);
+    const uint32_t fold = A.fold, m1 = A.mul_lo, c8 = A.mul_hi; // c8 = 2^8: umulhi(w, 2^8) = w >> 24 on the FMA pipe
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned long long local_cnt = 0;
+    uint32_t qn = 0; // entries in this warp's queue (warp-uniform, lives in a register)
+    constexpr uint64_t tile = (uint64_t)THREADS * UNROLL;
+    const uint64_t stride = (uint64_t)gridDim.x * tile;
+
+    // warp-aggregated push of one candidate group per hitting lane, then verify whenever a full batch is queued
+    auto push = [&](uint32_t hit, uint64_t g) {
+        const uint32_t b = __ballot_sync(0xffffffffu, hit != 0);
+        if (b)
+        {
+            if (hit) s_q[qn + __popc(b & lt_mask)] = g;
+            qn += __popc(b);
+            if (qn >= 32)
+            {
+                __syncwarp();
+                qn -= 32;
+                local_cnt += tri4_verify_groups<FOLD>(A, s_base, s_q[qn + lane], true);
+                __syncwarp();
+            }
+        }
+    };
+
+    // Register double buffering (see k_ac_scan): batch i is moved out of the landing registers, batch i+1 is issued,
+    // batch i is filtered.
+    uint64_t g0 = A.group_begin + (uint64_t)blockIdx.x * tile;
+    uint4 vn[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) vn[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (g0 + tile <= A.group_end)
+    {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) vn[u] = ld_vec_ordered(t4 + g0 + (uint64_t)u * THREADS + threadIdx.x);
+    }
+    for (; g0 + tile <= A.group_end; g0 += stride)
+    {
+        uint4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+        {
+            v[u] = vn[u];
+            asm volatile("" ::"r"(v[u].x), "r"(v[u].y), "r"(v[u].z), "r"(v[u].w));
+        }
+        const uint64_t gn = g0 + stride;
+        if (gn + tile <= A.group_end)
+        {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) vn[u] = ld_vec_ordered(t4 + gn + (uint64_t)u * THREADS + threadIdx.x);
+        }
+        uint32_t hit[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) hit[u] = tri4_filter<FOLD>(s_base, v[u], fold, m1, nbytes, c8);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) push(hit[u], g0 + (uint64_t)u * THREADS + threadIdx.x);
+    }
+    if (g0 < A.group_end) // ragged tile: lanes past the end re-read the last group and report no hit
+    {
+        for (int u = 0; u < UNROLL; u++)
+        {
+            const uint64_t g = g0 + (uint64_t)u * THREADS + threadIdx.x;
+            const uint64_t gc = g < A.group_end ? g : A.group_end - 1;
+            const uint32_t hit = tri4_filter<FOLD>(s_base, __ldg(t4 + gc), fold, m1, nbytes, c8);
+            push(g < A.group_end ? hit : 0u, g);
+        }
+    }
+    __syncwarp();
+    if (qn) local_cnt += tri4_verify_groups<FOLD>(A, s_base, lane < qn ? s_q[lane] : 0, lane < qn);
+    // tail: occurrences whose aligned window position lies beyond the last full group — brute force, lanes over patterns
+    if (blockIdx.x == 0 && threadIdx.x < 32)
+    {
+        const uint64_t first = A.tail_a >= 3 ? A.tail_a - 3 : 0;
+        for (uint64_t p = first; p < A.avail_len; p++)
+        {
+            const uint64_t a = (p + 3) / 4 * 4;
+            if (a < A.tail_a) continue;
+            for (uint32_t k = threadIdx.x; k < A.npat; k += 32) local_cnt += ac_verify_emit(A, k, (long long)p);
+        }
+    }
+    if (!A.want_positions)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local_cnt += __shfl_xor_sync(0xffffffffu, local_cnt, o);
+        if (lane == 0 && local_cnt) atomicAdd(A.counter, local_cnt);
+    }
+}
+
 // ------------------------------------------------------------------------------------- build
 static uint64_t pat_window(const uint8_t *p, uint32_t w, uint32_t fold)
 {
@@ -519,7 +704,10 @@ int ac_build_tables(Plan *plan)
     plan->min_len = lmin;
     plan->max_len = lmax;
     uint32_t w, s;
-    if (lmin >= 11) { w = 8; s = 4; }
+    const bool tri4 = lmin == 6;
+    T->tri4 = tri4;
+    if (tri4) { w = 3; s = 4; }
+    else if (lmin >= 11) { w = 8; s = 4; }
     else if (lmin >= 7) { w = lmin - 3; s = 4; }
     else if (lmin >= 5) { w = lmin - 1; s = 2; }
     else { w = lmin ? lmin : 1; s = 1; }
@@ -531,6 +719,12 @@ int ac_build_tables(Plan *plan)
     T->mul_lo = w >= 4 ? HC1 : (HC1 << (8 * (4 - w)));
     T->mul_hi = w > 4 ? (w >= 8 ? HC2 : (HC2 << (8 * (8 - w)))) : 0u;
     T->bit_shift = w >= 4 ? 0u : 8 * (4 - w);
+    if (tri4) // k_ac_tri4: mul_lo drops byte 3 of the word, mul_hi = 2^8 (w >> 24 on the FMA pipe), mul_b = "wild entries exist"
+    {
+        T->mul_lo = HC1 << 8;
+        T->mul_hi = 1u << 8;
+        T->mul_b = 0;
+    }
     if (s == 2) // paired scheme (ac_pair_filter): mT masks T to w-2 bytes, mA to 2 bytes, mB to w-2 bytes
     {
         T->mul_lo = HC1 << (8 * (4 - (w - 2)));
@@ -555,7 +749,22 @@ int ac_build_tables(Plan *plan)
             pv.push_back(pb[i] & m);
         }
         if (len[k] == 0) continue;
-        for (uint32_t d = 0; d < s; d++) ents.push_back({pat_window(pb + d, w, T->fold) & T->wmask, (k << 2) | d});
+        for (uint32_t d = 0; d < s; d++)
+        {
+            if (tri4)
+            {
+                // entries that know byte a+3 are keyed by the whole aligned word, the others ((len, d) = (6, 3)) by
+                // 1 << 32 | trigram
+                if (len[k] - d >= 4) ents.push_back({pat_window(pb + d, 4, T->fold), (k << 2) | d});
+                else
+                {
+                    ents.push_back({(1ull << 32) | (pat_window(pb + d, 3, T->fold) & 0xFFFFFFull), (k << 2) | d});
+                    T->mul_b = 1;
+                }
+            }
+            else
+                ents.push_back({pat_window(pb + d, w, T->fold) & T->wmask, (k << 2) | d});
+        }
     }
     std::stable_sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.key < b.key; });
     size_t distinct = 0;
@@ -564,8 +773,17 @@ int ac_build_tables(Plan *plan)
     // bitmap size (bytes, any multiple of 16 — addresses come from mulhi, not masking): keep the false-positive
     // rate of one lookup around 0.2 % or better, 16 KB .. 192 KB of the SM's 227 KB shared memory
     uint32_t nby = 16u << 10;
-    while (nby < (128u << 10) && (double)distinct / (double)(nby * 8.0) > 0.002) nby *= 2;
-    if (nby == (128u << 10) && (double)distinct / (double)(nby * 8.0) > 0.0015) nby = 192u << 10;
+    if (tri4)
+    {
+        // one 32-bit word per trigram: keep word occupancy around 7 % or less
+        while (nby < (128u << 10) && distinct * 56.0 > (double)nby) nby *= 2;
+        if (nby == (128u << 10) && distinct * 56.0 > (double)nby) nby = 192u << 10;
+    }
+    else
+    {
+        while (nby < (128u << 10) && (double)distinct / (double)(nby * 8.0) > 0.002) nby *= 2;
+        if (nby == (128u << 10) && (double)distinct / (double)(nby * 8.0) > 0.0015) nby = 192u << 10;
+    }
     T->bitmap_bytes = nby;
     std::vector<uint32_t> bitmap(nby / 4, 0);
     uint32_t nslots = 16;
@@ -578,7 +796,12 @@ int ac_build_tables(Plan *plan)
         size_t j = i;
         while (j < ents.size() && ents[j].key == ents[i].key) { list[j] = ents[j].e; j++; }
         const uint32_t lo = (uint32_t)ents[i].key, hi = (uint32_t)(ents[i].key >> 32);
-        if (s == 2)
+        if (tri4)
+        {
+            const uint32_t wi = (uint32_t)(((uint64_t)((lo & 0xFFFFFFu) * T->mul_lo) * nby) >> 32) >> 2;
+            bitmap[wi] |= hi ? 0xFFFFFFFFu : (1u << ((lo >> 24) & 31u));
+        }
+        else if (s == 2)
         {
             // window bytes c0..c(w-1) as a 64-bit little-endian value
             const uint64_t c = ents[i].key;
@@ -622,7 +845,8 @@ int ac_build_tables(Plan *plan)
         CKB(cudaMemcpy(T->d_pat_len, len.data(), K * 4, cudaMemcpyHostToDevice));
     }
     char name[96];
-    snprintf(name, sizeof name, "window%u/stride%u%s bitmap %uKB%s", w, s, s == 2 ? " paired" : "", nby >> 10, plan->case_sensitive ? "" : " fold");
+    snprintf(name, sizeof name, "window%u/stride%u%s bitmap %uKB%s", w, s, tri4 ? " tri4+byte-select" : (s == 2 ? " paired" : ""), nby >> 10,
+             plan->case_sensitive ? "" : " fold");
     plan->filter_name = name;
     return 0;
 }
@@ -685,8 +909,35 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     if (A.group_end > total_groups) A.group_end = total_groups;
     if (A.group_begin > A.group_end) A.group_begin = A.group_end;
 
-    constexpr int THREADS = 640, UNROLL = 4;
     static int sm_count = 0;
+    if (!sm_count)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (T->tri4)
+    {
+        constexpr int THREADS = 768, UNROLL = 4;
+        const uint64_t full_groups = a.avail_len / 16; // a lookup only needs its own aligned word
+        A.tail_a = full_groups * 16;
+        A.group_begin = a.own_begin / 16;
+        A.group_end = (a.own_end + 3) / 16 + 1; // aligned window position of an owned start lies < own_end + 4
+        if (A.group_end > full_groups) A.group_end = full_groups;
+        if (A.group_begin > A.group_end) A.group_begin = A.group_end;
+        const size_t smem = (size_t)T->bitmap_bytes + (size_t)(THREADS / 32) * 64 * sizeof(uint64_t);
+        auto kernel = T->fold != 0xFFFFFFFFu ? k_ac_tri4<true, THREADS, UNROLL> : k_ac_tri4<false, THREADS, UNROLL>;
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const uint64_t groups = A.group_end - A.group_begin;
+        const uint64_t tile = (uint64_t)THREADS * UNROLL;
+        uint64_t blocks = (groups + tile - 1) / tile;
+        if (blocks == 0) blocks = 1;
+        if (blocks > (uint64_t)sm_count) blocks = sm_count;
+        kernel<<<(unsigned)blocks, THREADS, smem, st>>>(A);
+        count_launch();
+        return;
+    }
+    constexpr int THREADS = 640, UNROLL = 4;
     const size_t smem = (size_t)T->bitmap_bytes + 128 + (size_t)(THREADS / 32) * AcQueue<UNROLL>::CAP * sizeof(uint64_t);
     auto kernel = [&]() -> void (*)(AcDev) {
         const bool f = T->fold != 0xFFFFFFFFu;
@@ -694,12 +945,6 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
         if (T->s == 2) return f ? k_ac_scan<2, true, THREADS, UNROLL> : k_ac_scan<2, false, THREADS, UNROLL>;
         return f ? k_ac_scan<4, true, THREADS, UNROLL> : k_ac_scan<4, false, THREADS, UNROLL>;
     }();
-    if (!sm_count)
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const uint64_t groups = A.group_end - A.group_begin;
     const uint64_t tile = (uint64_t)THREADS * UNROLL;
