@@ -499,8 +499,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
 // instructions of the stride-2 paired filter above.  A lookup passes for ~1 % of the positions of English-like text
 // against 1000 patterns; those groups are queued per warp and verified 32 at a time against the exact table below.
 //
-// Exact table (L2 resident, same AcSlot open addressing): key = the folded word w for entries that know byte a+3,
-// key = (1 << 32) | trigram for those that do not; value = list of (pattern << 2 | d).
+// Exact table (L2 resident, AcSlot open addressing): key = the folded first 6 bytes of a pattern, value = list of the
+// pattern indices that start with them.
 // =============================================================================================
 template <bool FOLD>
 __device__ __forceinline__ uint32_t tri4_filter(uint32_t s_base, const uint4 &v, uint32_t fold, uint32_t m1, uint32_t nbytes,
@@ -519,41 +519,62 @@ __device__ __forceinline__ uint32_t tri4_filter(uint32_t s_base, const uint4 &v,
     return acc & 1u;
 }
 
-// one candidate group per lane (valid lanes only); every lane walks its own hits, probes and pattern compares
+// One candidate group per lane.  A lookup that passed says "some pattern may contain this aligned word at offset d";
+// all patterns have >= 6 bytes here, so each of the four possible starts p = a - d is tested by looking its 6 bytes
+// [p, p+6) up in the exact prefix table (4 independent L2 probes, almost always an empty slot), and only a prefix hit
+// goes on to the full compare.  The 24 bytes around the group come from L2 (the streaming loads keep them there).
+__device__ __forceinline__ uint32_t prefix_hash(uint32_t lo, uint32_t hi) { return lo * HC1 + hi * HC2; }
+
 template <bool FOLD>
 __device__ __noinline__ unsigned tri4_verify_groups(const AcDev &A, uint32_t s_base, uint64_t g, bool valid)
 {
     unsigned n = 0;
     if (!valid) return 0;
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(A.text) + g);
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint4 *t4 = reinterpret_cast<const uint4 *>(A.text);
+    const uint4 v = __ldg(t4 + g);
+    uint32_t X[6]; // bytes [16g-4, 16g+20): previous word, the group, next word
+    X[0] = g > 0 ? __ldg(reinterpret_cast<const uint32_t *>(t4 + g) - 1) : 0u;
+    X[1] = v.x; X[2] = v.y; X[3] = v.z; X[4] = v.w;
+    X[5] = 0;
+    {
+        const uint64_t nb = (g + 1) * 16;
+        if (nb + 4 <= A.avail_len) X[5] = __ldg(reinterpret_cast<const uint32_t *>(t4 + g + 1));
+        else
+            for (uint64_t i = nb; i < A.avail_len; i++) X[5] |= (uint32_t)A.text[i] << (8 * (i - nb));
+    }
+    const uint32_t fold = A.fold, nslots = A.nslots, m1 = A.mul_lo, nbytes = A.bitmap_bytes;
+    if (FOLD)
+    {
+#pragma unroll
+        for (int i = 0; i < 6; i++) X[i] &= fold;
+    }
+    const AcSlot *__restrict__ slots = A.slots;
 #pragma unroll
     for (int k = 0; k < 4; k++)
     {
-        if (FOLD) w[k] &= A.fold;
-        const uint32_t word = lds_u32(s_base + (__umulhi(w[k] * A.mul_lo, A.bitmap_bytes) & ~3u));
-        if (!((word >> ((w[k] >> 24) & 31u)) & 1u)) continue;
-        const uint64_t a = g * 16 + 4 * k;
-        // probe 0: entries that know byte a+3 (key = w); probe 1: entries that do not (key = 1<<32 | trigram)
-        for (int wild = 0; wild < (A.mul_b ? 2 : 1); wild++)
+        const uint32_t w = X[k + 1];
+        const uint32_t word = lds_u32(s_base + (__umulhi(w * m1, nbytes) & ~3u));
+        if (!((word >> ((w >> 24) & 31u)) & 1u)) continue;
+        const long long a = (long long)(g * 16 + 4 * k);
+#pragma unroll
+        for (int d = 0; d < 4; d++)
         {
-            const uint32_t lo = wild ? (w[k] & 0x00FFFFFFu) : w[k], hi = (uint32_t)wild;
+            // 6 bytes at byte offset 4(k+1) - d of X
+            const int j = d ? k : k + 1, r = (4 - d) & 3;
+            const uint32_t lo = r ? __funnelshift_r(X[j], X[j + 1], 8 * r) : X[j];
+            const uint32_t hi = (r ? __funnelshift_r(X[j + 1], j + 2 < 6 ? X[j + 2] : 0u, 8 * r) : X[j + 1]) & 0xFFFFu;
             const uint64_t key = ((uint64_t)hi << 32) | lo;
-            uint32_t h = slot_hash(lo, hi) & (A.nslots - 1);
+            uint32_t h = prefix_hash(lo, hi) & (nslots - 1);
             for (;;)
             {
-                const AcSlot sl = A.slots[h];
+                const AcSlot sl = slots[h];
                 if (sl.count == 0) break;
                 if (sl.key == key)
                 {
-                    for (uint32_t i = 0; i < sl.count; i++)
-                    {
-                        const uint32_t e = A.list[sl.first + i];
-                        n += ac_verify_emit(A, e >> 2, (long long)a - (long long)(e & 3));
-                    }
+                    for (uint32_t i = 0; i < sl.count; i++) n += ac_verify_emit(A, A.list[sl.first + i], a - d);
                     break;
                 }
-                h = (h + 1) & (A.nslots - 1);
+                h = (h + 1) & (nslots - 1);
             }
         }
     }
@@ -719,7 +740,7 @@ int ac_build_tables(Plan *plan)
     T->mul_lo = w >= 4 ? HC1 : (HC1 << (8 * (4 - w)));
     T->mul_hi = w > 4 ? (w >= 8 ? HC2 : (HC2 << (8 * (8 - w)))) : 0u;
     T->bit_shift = w >= 4 ? 0u : 8 * (4 - w);
-    if (tri4) // k_ac_tri4: mul_lo drops byte 3 of the word, mul_hi = 2^8 (w >> 24 on the FMA pipe), mul_b = "wild entries exist"
+    if (tri4) // k_ac_tri4: mul_lo drops byte 3 of the word, mul_hi = 2^8 (w >> 24 on the FMA pipe)
     {
         T->mul_lo = HC1 << 8;
         T->mul_hi = 1u << 8;
@@ -737,6 +758,7 @@ int ac_build_tables(Plan *plan)
     std::vector<uint8_t> pv, pm;
     struct Ent { uint64_t key; uint32_t e; };
     std::vector<Ent> ents;
+    std::vector<std::pair<uint32_t, uint32_t>> tri_bits; // tri4: (trigram, bits to set in its word)
     for (uint32_t k = 0; k < K; k++)
     {
         off[k] = (uint32_t)pv.size();
@@ -749,22 +771,19 @@ int ac_build_tables(Plan *plan)
             pv.push_back(pb[i] & m);
         }
         if (len[k] == 0) continue;
-        for (uint32_t d = 0; d < s; d++)
+        if (tri4)
         {
-            if (tri4)
+            // exact table of k_ac_tri4: keyed by the (folded) first 6 bytes of the pattern, value = pattern index
+            ents.push_back({pat_window(pb, 6, T->fold) & 0xFFFFFFFFFFFFull, k});
+            for (uint32_t d = 0; d < 4; d++)
             {
-                // entries that know byte a+3 are keyed by the whole aligned word, the others ((len, d) = (6, 3)) by
-                // 1 << 32 | trigram
-                if (len[k] - d >= 4) ents.push_back({pat_window(pb + d, 4, T->fold), (k << 2) | d});
-                else
-                {
-                    ents.push_back({(1ull << 32) | (pat_window(pb + d, 3, T->fold) & 0xFFFFFFull), (k << 2) | d});
-                    T->mul_b = 1;
-                }
+                const uint32_t tri = (uint32_t)pat_window(pb + d, 3, T->fold) & 0xFFFFFFu;
+                // (len, d) = (6, 3) does not know byte a+3: all 32 bits
+                tri_bits.push_back({tri, len[k] - d >= 4 ? (1u << ((pb[d + 3] & T->fold) & 31u)) : 0xFFFFFFFFu});
             }
-            else
-                ents.push_back({pat_window(pb + d, w, T->fold) & T->wmask, (k << 2) | d});
+            continue;
         }
+        for (uint32_t d = 0; d < s; d++) ents.push_back({pat_window(pb + d, w, T->fold) & T->wmask, (k << 2) | d});
     }
     std::stable_sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.key < b.key; });
     size_t distinct = 0;
@@ -776,8 +795,12 @@ int ac_build_tables(Plan *plan)
     if (tri4)
     {
         // one 32-bit word per trigram: keep word occupancy around 7 % or less
-        while (nby < (128u << 10) && distinct * 56.0 > (double)nby) nby *= 2;
-        if (nby == (128u << 10) && distinct * 56.0 > (double)nby) nby = 192u << 10;
+        std::vector<uint32_t> tris;
+        for (auto &tb : tri_bits) tris.push_back(tb.first);
+        std::sort(tris.begin(), tris.end());
+        const double ntri = (double)(std::unique(tris.begin(), tris.end()) - tris.begin());
+        while (nby < (128u << 10) && ntri * 56.0 > (double)nby) nby *= 2;
+        if (nby == (128u << 10) && ntri * 56.0 > (double)nby) nby = 192u << 10;
     }
     else
     {
@@ -798,8 +821,6 @@ int ac_build_tables(Plan *plan)
         const uint32_t lo = (uint32_t)ents[i].key, hi = (uint32_t)(ents[i].key >> 32);
         if (tri4)
         {
-            const uint32_t wi = (uint32_t)(((uint64_t)((lo & 0xFFFFFFu) * T->mul_lo) * nby) >> 32) >> 2;
-            bitmap[wi] |= hi ? 0xFFFFFFFFu : (1u << ((lo >> 24) & 31u));
         }
         else if (s == 2)
         {
@@ -820,11 +841,12 @@ int ac_build_tables(Plan *plan)
             const uint32_t bit = (s == 1 ? (hsh >> T->bit_shift) : hsh) & 7;
             bitmap[baddr >> 2] |= 1u << (8 * (baddr & 3) + bit);
         }
-        uint32_t h = slot_hash(lo, hi) & (nslots - 1);
+        uint32_t h = (tri4 ? lo * HC1 + hi * HC2 : slot_hash(lo, hi)) & (nslots - 1);
         while (slots[h].count) h = (h + 1) & (nslots - 1);
         slots[h] = AcSlot{ents[i].key, (uint32_t)i, (uint32_t)(j - i)};
         i = j;
     }
+    for (auto &tb : tri_bits) bitmap[(uint32_t)(((uint64_t)(tb.first * T->mul_lo) * nby) >> 32) >> 2] |= tb.second;
     if (pv.empty()) { pv.push_back(0); pm.push_back(0); }
     if (list.empty()) list.push_back(0);
     CKB(cudaMalloc(&T->d_bitmap, bitmap.size() * 4));

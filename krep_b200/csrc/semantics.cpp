@@ -261,18 +261,31 @@ static uint64_t replay_memchr_short(const search_params_t *P, bool only_matching
     return cnt;
 }
 
-// simd_sse42_search, krep.c:4702-4869 (preconditions already resolved by the caller)
+// simd_sse42_search, krep.c:4702-4869 (preconditions already resolved by the caller).  The scan slides a window of
+// min(16, remaining) bytes by chunk-m+1 until it holds a full match, so it always reports the first occurrence at or
+// after the cursor; the window start itself only shows in -c mode, where the jump to the next line is computed from
+// the match offset but added to the window start (krep.c:4791-4795) — it lands `index` bytes before the next line.
 static uint64_t replay_sse42(const search_params_t *P, bool only_matching, size_t m, Cursor c, const char *t, size_t n,
                              match_result_t *res)
 {
     if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
     uint64_t cnt = 0;
     size_t last_line = SIZE_MAX, cur = 0;
+    const size_t step = 17 - m; // window advance on a miss while 16 bytes remain (krep.c:4858); m <= 16
     while (n - cur >= m)
     {
         const size_t j = c.next_full(cur);
         if (j == c.n) break;
         const size_t s = c.pos(j);
+        size_t wcur = cur; // start of the window in which s is found
+        for (;;)
+        {
+            const size_t rem = n - wcur, chunk = rem < 16 ? rem : 16;
+            if (s - wcur <= chunk - m) break; // always true once fewer than 16 bytes remain (s + m <= n)
+            const size_t k1 = (s - wcur - (16 - m) + step - 1) / step; // windows until the occurrence fits
+            const size_t k2 = (n - 16 - wcur) / step + 1;              // windows until fewer than 16 bytes remain
+            wcur += (k1 < k2 ? k1 : k2) * step;
+        }
         if (!P->whole_word || c.ww(j))
         {
             bool bumped = false;
@@ -284,7 +297,7 @@ static uint64_t replay_sse42(const search_params_t *P, bool only_matching, size_
                     if (cnt >= P->max_count) break;
                     cnt++; last_line = ls; bumped = true;
                     const size_t le = line_end(t, n, ls);
-                    if (le < n) { cur = le + 1; continue; }
+                    if (le < n) { cur = wcur + ((le + 1) - s); continue; }
                 }
             }
             else

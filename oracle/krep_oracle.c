@@ -322,12 +322,18 @@ uint64_t oracle_memchr_short_search(const search_params_t *P, const char *text, 
 
 /* ==========================================================================
  * simd_sse42_search — krep.c:4702-4869 (case-sensitive, pattern_len <= 16).
- * _mm_cmpestri(EQUAL_ORDERED) over a 16-byte window returns the first index
- * at which the pattern matches fully or as a prefix cut by the window end;
- * a hit is accepted only if it is a full match (krep.c:4761), otherwise the
- * window slides by 16-m+1, so the scan sees exactly "first occurrence at or
- * after the cursor".  After an accepted OR -w-rejected occurrence the cursor
- * moves to match+m (default) or match+1 (only_matching) — krep.c:4839-4848.
+ * _mm_cmpestri(EQUAL_ORDERED) over a window of min(16, remaining) bytes returns
+ * the first index at which the pattern matches fully or as a prefix cut by the
+ * window end; a hit is accepted only if it is a full match (krep.c:4761) —
+ * full matches have smaller indices than cut ones, so that is "the first full
+ * match inside the window" — otherwise the window slides by chunk-m+1
+ * (krep.c:4858).  After an accepted OR -w-rejected occurrence the cursor moves
+ * to match+m (default) or match+1 (only_matching) — krep.c:4839-4848.
+ * The window position is observable in -c mode: after counting a line the
+ * cursor advances by (line_end+1 - match_start) FROM THE WINDOW START
+ * (krep.c:4791-4795: the advance is computed from the match offset but added to
+ * current_pos), i.e. it lands `index` bytes before the next line, so the windows
+ * are restated literally.
  * Any other precondition falls back to boyer_moore_search (krep.c:4708).
  * ========================================================================== */
 uint64_t oracle_sse42_search(const search_params_t *P, const char *text, size_t n, match_result_t *res)
@@ -337,11 +343,21 @@ uint64_t oracle_sse42_search(const search_params_t *P, const char *text, size_t 
     if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
     const unsigned char *t = (const unsigned char *)text, *p = (const unsigned char *)P->pattern;
     uint64_t cnt = 0;
-    size_t last_line = SIZE_MAX, cur = 0;
-    while (n - cur >= m)
+    size_t last_line = SIZE_MAX, cur = 0, rem = n;
+    while (rem >= m)
     {
-        size_t s = next_occ(t, n, p, m, true, cur);
-        if (s == SIZE_MAX) break;
+        const size_t chunk = rem < 16 ? rem : 16;
+        size_t idx = SIZE_MAX;
+        for (size_t i = 0; i + m <= chunk; i++)
+            if (occurs(t + cur + i, p, m, true)) { idx = i; break; }
+        if (idx == SIZE_MAX)
+        {
+            size_t adv = chunk > m ? chunk - m + 1 : 1; /* krep.c:4858 */
+            if (adv > rem) adv = rem;
+            cur += adv; rem -= adv;
+            continue;
+        }
+        const size_t s = cur + idx;
         if (!P->whole_word || whole_word(text, n, s, s + m))
         {
             bool bumped = false;
@@ -353,7 +369,12 @@ uint64_t oracle_sse42_search(const search_params_t *P, const char *text, size_t 
                     if (cnt >= P->max_count) break;
                     cnt++; last_line = ls; bumped = true;
                     size_t le = line_end(text, n, ls);
-                    if (le < n) { cur = le + 1; continue; } /* krep.c:4787-4797 (advance > 0 always) */
+                    if (le < n)
+                    {
+                        size_t adv = (le + 1) - s; /* > 0: no newline in [line_start, s) */
+                        cur += adv; rem -= adv;     /* krep.c:4795: added to the window start, not to the match */
+                        continue;
+                    }
                 }
             }
             else
@@ -364,8 +385,13 @@ uint64_t oracle_sse42_search(const search_params_t *P, const char *text, size_t 
             }
             if (bumped && cnt >= P->max_count) break;
         }
-        cur = g_only_matching ? s + 1 : s + m;
-        if (cur > n) cur = n;
+        size_t adv = idx + 1;
+        if (!g_only_matching)
+        {
+            adv = idx + m;
+            if (adv > rem) adv = rem;
+        }
+        cur += adv; rem -= adv;
     }
     return cnt;
 }

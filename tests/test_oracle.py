@@ -111,9 +111,10 @@ def random_case(rng, func):
         lo, hi = {"memchr": (1, 1), "memchr_short": (2, 3), "sse42": (1, 18), "avx2": (14, 36),
                   "avx512": (28, 70)}.get(func, (1, 20))
         m = rng.randint(lo, hi)
-        if func in ("avx2", "avx512") and rng.random() < 0.5:
+        if (func in ("avx2", "avx512") and rng.random() < 0.5) or rng.random() < 0.25:
             # periodic needle + periodic text: many overlapping occurrences, window / tail edges everywhere
             unit = bytes(rng.choice(alpha) for _ in range(rng.randint(1, 3)))
+            m = min(m, rng.choice([m, m, 2, 3, 4, 6]))
             n = rng.choice([31, 32, 33, 47, 63, 64, 65, 90, 96, 127, 128, 129, 200, 257])
             text = bytearray((unit * (n // len(unit) + 1))[:n])
             for _ in range(rng.randint(0, 4)):
