@@ -37,6 +37,7 @@ struct AcSlot
 struct AcDevTables
 {
     uint32_t *d_bitmap = nullptr; // 2^B bits
+    uint8_t *d_bitmap2 = nullptr; // tri4: 2^23-bit second-level filter over the 6-byte prefixes (L2 resident)
     AcSlot *d_slots = nullptr;    // nslots (power of two)
     uint32_t *d_list = nullptr;   // (pattern << 2) | d
     uint8_t *d_pool_val = nullptr, *d_pool_mask = nullptr;
@@ -51,6 +52,7 @@ struct AcDevTables
 struct AcDev
 {
     const uint32_t *bitmap;
+    const uint8_t *bitmap2;
     const AcSlot *slots;
     const uint32_t *list;
     const uint8_t *pool_val, *pool_mask;
@@ -158,6 +160,12 @@ __device__ __forceinline__ uint32_t ld_u32_ordered(const uint32_t *p)
 {
     uint32_t v;
     asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_u8_ordered(const uint8_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ uint2 ld_u64_ordered(const uint2 *p)
@@ -497,10 +505,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
 // and the (L = 6, d = 3) entries, which do not know byte a+3, set all 32 bits of their word.  Per 16 bytes that is
 // 4 lookups of ~7 instructions split evenly between the FMA and ALU pipes, and 4 shared-memory loads — half the
 // instructions of the stride-2 paired filter above.  A lookup passes for ~1 % of the positions of English-like text
-// against 1000 patterns; those groups are queued per warp and verified 32 at a time against the exact table below.
+// against 1000 patterns; those groups are queued per warp and verified 32 at a time:
 //
 // Exact table (L2 resident, AcSlot open addressing): key = the folded first 6 bytes of a pattern, value = list of the
-// pattern indices that start with them.
+// pattern indices that start with them.  A passed lookup at aligned position a means "some pattern may contain this
+// word at offset d", so each of the four starts p = a - d is tested by probing its 6 bytes [p, p+6) — four independent
+// L2 loads issued together, almost always an empty slot — and only a prefix hit goes on to the full compare.
 // =============================================================================================
 template <bool FOLD>
 __device__ __forceinline__ uint32_t tri4_filter(uint32_t s_base, const uint4 &v, uint32_t fold, uint32_t m1, uint32_t nbytes,
@@ -519,63 +529,109 @@ __device__ __forceinline__ uint32_t tri4_filter(uint32_t s_base, const uint4 &v,
     return acc & 1u;
 }
 
-// One candidate group per lane.  A lookup that passed says "some pattern may contain this aligned word at offset d";
-// all patterns have >= 6 bytes here, so each of the four possible starts p = a - d is tested by looking its 6 bytes
-// [p, p+6) up in the exact prefix table (4 independent L2 probes, almost always an empty slot), and only a prefix hit
-// goes on to the full compare.  The 24 bytes around the group come from L2 (the streaming loads keep them there).
 __device__ __forceinline__ uint32_t prefix_hash(uint32_t lo, uint32_t hi) { return lo * HC1 + hi * HC2; }
 
+// Queue entry: (group index relative to group_begin) << 4 | mask of the lookups still to verify (0 = not known yet).
+// One entry per lane.  Every lane verifies ONE passed lookup per call; a group with more than one puts the rest back
+// into the queue, so a batch costs two L2 round trips (the 24 bytes around the group, then the four prefix probes).
+// Inlined into the scan kernel at its single drain site: a call would force the prefetched vectors of the streaming
+// loop through the ABI's few callee-saved registers, i.e. into local memory on every iteration.
 template <bool FOLD>
-__device__ __noinline__ unsigned tri4_verify_groups(const AcDev &A, uint32_t s_base, uint64_t g, bool valid)
+__device__ __forceinline__ unsigned tri4_verify_batch(const AcDev &A, uint32_t s_base, uint64_t entry, bool valid, uint64_t *s_q,
+                                                       uint32_t &qn, uint32_t lt_mask)
 {
     unsigned n = 0;
-    if (!valid) return 0;
-    const uint4 *t4 = reinterpret_cast<const uint4 *>(A.text);
-    const uint4 v = __ldg(t4 + g);
-    uint32_t X[6]; // bytes [16g-4, 16g+20): previous word, the group, next word
-    X[0] = g > 0 ? __ldg(reinterpret_cast<const uint32_t *>(t4 + g) - 1) : 0u;
-    X[1] = v.x; X[2] = v.y; X[3] = v.z; X[4] = v.w;
-    X[5] = 0;
+    uint32_t X[6] = {0, 0, 0, 0, 0, 0}; // bytes [16g-4, 16g+20): previous word, the group, next word
+    uint32_t km = (uint32_t)entry & 15u;
+    const uint64_t g = A.group_begin + (entry >> 4);
+    if (valid)
     {
+        const uint4 *t4 = reinterpret_cast<const uint4 *>(A.text);
+        const uint4 v = __ldg(t4 + g);
+        X[0] = g > 0 ? __ldg(reinterpret_cast<const uint32_t *>(t4 + g) - 1) : 0u;
         const uint64_t nb = (g + 1) * 16;
         if (nb + 4 <= A.avail_len) X[5] = __ldg(reinterpret_cast<const uint32_t *>(t4 + g + 1));
         else
             for (uint64_t i = nb; i < A.avail_len; i++) X[5] |= (uint32_t)A.text[i] << (8 * (i - nb));
-    }
-    const uint32_t fold = A.fold, nslots = A.nslots, m1 = A.mul_lo, nbytes = A.bitmap_bytes;
-    if (FOLD)
-    {
+        X[1] = v.x; X[2] = v.y; X[3] = v.z; X[4] = v.w;
+        if (FOLD)
+        {
 #pragma unroll
-        for (int i = 0; i < 6; i++) X[i] &= fold;
-    }
-    const AcSlot *__restrict__ slots = A.slots;
+            for (int i = 0; i < 6; i++) X[i] &= A.fold;
+        }
+        if (km == 0)
+        {
 #pragma unroll
-    for (int k = 0; k < 4; k++)
+            for (int k = 0; k < 4; k++)
+            {
+                const uint32_t w = X[k + 1];
+                const uint32_t word = lds_u32(s_base + (__umulhi(w * A.mul_lo, A.bitmap_bytes) & ~3u));
+                km |= ((word >> ((w >> 24) & 31u)) & 1u) << k;
+            }
+        }
+    }
+    const int k = km ? __ffs(km) - 1 : 0;
+    const bool work = km != 0;
+    km &= km - 1;
     {
-        const uint32_t w = X[k + 1];
-        const uint32_t word = lds_u32(s_base + (__umulhi(w * m1, nbytes) & ~3u));
-        if (!((word >> ((w >> 24) & 31u)) & 1u)) continue;
-        const long long a = (long long)(g * 16 + 4 * k);
+        // lookups beyond the first go back into the queue (room is guaranteed: this batch just left it)
+        const uint32_t b = __ballot_sync(0xffffffffu, km != 0);
+        if (b)
+        {
+            if (km) s_q[qn + __popc(b & lt_mask)] = (entry & ~15ull) | km;
+            qn += __popc(b);
+        }
+    }
+    if (!work) return 0;
+    // words X[k], X[k+1], X[k+2] without dynamic register indexing
+    uint32_t y0 = X[0], y1 = X[1], y2 = X[2];
+    if (k == 1) { y0 = X[1]; y1 = X[2]; y2 = X[3]; }
+    if (k == 2) { y0 = X[2]; y1 = X[3]; y2 = X[4]; }
+    if (k == 3) { y0 = X[3]; y1 = X[4]; y2 = X[5]; }
+    const long long a = (long long)(g * 16 + 4 * k);
+    // start p = a - d: 6 bytes at byte offset 4 - d of (y0 y1 y2)
+    uint32_t lo[4], hi[4], h[4];
+    lo[0] = y1; hi[0] = y2 & 0xFFFFu;
+#pragma unroll
+    for (int d = 1; d < 4; d++)
+    {
+        lo[d] = __funnelshift_r(y0, y1, 8 * (4 - d));
+        hi[d] = __funnelshift_r(y1, y2, 8 * (4 - d)) & 0xFFFFu;
+    }
+    const uint32_t nmask = A.nslots - 1;
+    const AcSlot *slots = A.slots;
+    // second-level filter: one bit per 23-bit prefix hash in a 1 MB L2-resident bitmap; four byte loads issued together
+    uint32_t pass = 0;
+    {
+        uint32_t by[4];
 #pragma unroll
         for (int d = 0; d < 4; d++)
         {
-            // 6 bytes at byte offset 4(k+1) - d of X
-            const int j = d ? k : k + 1, r = (4 - d) & 3;
-            const uint32_t lo = r ? __funnelshift_r(X[j], X[j + 1], 8 * r) : X[j];
-            const uint32_t hi = (r ? __funnelshift_r(X[j + 1], j + 2 < 6 ? X[j + 2] : 0u, 8 * r) : X[j + 1]) & 0xFFFFu;
-            const uint64_t key = ((uint64_t)hi << 32) | lo;
-            uint32_t h = prefix_hash(lo, hi) & (nslots - 1);
-            for (;;)
+            h[d] = prefix_hash(lo[d], hi[d]);
+            by[d] = ld_u8_ordered(A.bitmap2 + (h[d] >> 12));
+        }
+#pragma unroll
+        for (int d = 0; d < 4; d++) pass |= ((by[d] >> ((h[d] >> 9) & 7u)) & 1u) << d;
+    }
+    if (pass == 0) return 0; // the common case: nothing starts with any of the four
+#pragma unroll 1
+    for (int d = 0; d < 4; d++)
+    {
+        if (!((pass >> d) & 1u)) continue;
+        const uint32_t lod = d == 0 ? lo[0] : (d == 1 ? lo[1] : (d == 2 ? lo[2] : lo[3]));
+        const uint32_t hid = d == 0 ? hi[0] : (d == 1 ? hi[1] : (d == 2 ? hi[2] : hi[3]));
+        uint32_t hh = (d == 0 ? h[0] : (d == 1 ? h[1] : (d == 2 ? h[2] : h[3]))) & nmask;
+        for (;;)
+        {
+            const AcSlot q = slots[hh];
+            if (q.count == 0) break;
+            if (q.key == (((uint64_t)hid << 32) | lod))
             {
-                const AcSlot sl = slots[h];
-                if (sl.count == 0) break;
-                if (sl.key == key)
-                {
-                    for (uint32_t i = 0; i < sl.count; i++) n += ac_verify_emit(A, A.list[sl.first + i], a - d);
-                    break;
-                }
-                h = (h + 1) & (nslots - 1);
+#pragma unroll 1
+                for (uint32_t i = 0; i < q.count; i++) n += ac_verify_emit(A, A.list[q.first + i], a - d);
+                break;
             }
+            hh = (hh + 1) & nmask;
         }
     }
     return n;
@@ -585,95 +641,134 @@ template <bool FOLD, int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ AcDev A)
 {
     extern __shared__ __align__(16) uint8_t s_mem[];
-    constexpr int QCAP = 64; // < 32 left over + at most 32 new per push
+    constexpr int QCAP = 32 * UNROLL + 32; // < 32 left over + at most 32 new per vector of the batch
+    constexpr uint32_t TILE = (uint32_t)THREADS * UNROLL;
     const uint32_t nbytes = A.bitmap_bytes;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t *s_q = reinterpret_cast<uint64_t *>(s_mem + nbytes) + warp * QCAP;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(A.bitmap);
         uint4 *dst = reinterpret_cast<uint4 *>(s_mem);
-        for (uint32_t i = threadIdx.x; i < nbytes / 16; i += THREADS) dst[i] = src[i];
+        for (uint32_t i = tid; i < nbytes / 16; i += THREADS) dst[i] = src[i];
     }
     __syncthreads();
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_mem);
-    const uint4 *__restrict__ t4 = reinterpret_cast<const uint4 *>(A.text);
     const uint32_t fold = A.fold, m1 = A.mul_lo, c8 = A.mul_hi; // c8 = 2^8: umulhi(w, 2^8) = w >> 24 on the FMA pipe
     const uint32_t lt_mask = (1u << lane) - 1u;
     unsigned long long local_cnt = 0;
     uint32_t qn = 0; // entries in this warp's queue (warp-uniform, lives in a register)
-    constexpr uint64_t tile = (uint64_t)THREADS * UNROLL;
-    const uint64_t stride = (uint64_t)gridDim.x * tile;
 
-    // warp-aggregated push of one candidate group per hitting lane, then verify whenever a full batch is queued
-    auto push = [&](uint32_t hit, uint64_t g) {
+    // warp-aggregated push of one candidate group per hitting lane (rel = group index relative to group_begin)
+    auto push = [&](uint32_t hit, uint32_t rel) {
         const uint32_t b = __ballot_sync(0xffffffffu, hit != 0);
         if (b)
         {
-            if (hit) s_q[qn + __popc(b & lt_mask)] = g;
+            if (hit) s_q[qn + __popc(b & lt_mask)] = (uint64_t)rel << 4;
             qn += __popc(b);
-            if (qn >= 32)
-            {
-                __syncwarp();
-                qn -= 32;
-                local_cnt += tri4_verify_groups<FOLD>(A, s_base, s_q[qn + lane], true);
-                __syncwarp();
-            }
         }
     };
+    // verify queued candidates 32 at a time while at least `threshold` are waiting (32 in the loop, 1 at the end)
+    auto drain = [&](uint32_t threshold) {
+        while (qn >= threshold)
+        {
+            __syncwarp();
+            const uint32_t take = qn < 32 ? qn : 32;
+            qn -= take;
+            const bool valid = lane < take;
+            const uint64_t e = valid ? s_q[qn + lane] : 0;
+            __syncwarp();
+            local_cnt += tri4_verify_batch<FOLD>(A, s_base, e, valid, s_q, qn, lt_mask);
+        }
+    };
+    auto filter_push = [&](const uint4 (&v)[UNROLL], uint32_t rel0) {
+        uint32_t hm = 0; // bit u: vector u holds a passed lookup
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) hm |= tri4_filter<FOLD>(s_base, v[u], fold, m1, nbytes, c8) << u;
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) push((hm >> u) & 1u, rel0 + (uint32_t)u * THREADS);
+        drain(32);
+    };
+    auto touch = [](const uint4 (&v)[UNROLL]) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) asm volatile("" ::"r"(v[u].x), "r"(v[u].y), "r"(v[u].z), "r"(v[u].w));
+    };
 
-    // Register double buffering (see k_ac_scan): batch i is moved out of the landing registers, batch i+1 is issued,
-    // batch i is filtered.
-    uint64_t g0 = A.group_begin + (uint64_t)blockIdx.x * tile;
-    uint4 vn[UNROLL];
+    // This CTA owns the full tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; n_groups < 2^32 per launch (host splits).
+    const uint32_t n_groups = (uint32_t)(A.group_end - A.group_begin);
+    const uint32_t full_tiles = n_groups / TILE;
+    const uint32_t n_it = full_tiles > blockIdx.x ? (full_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t rel_step = gridDim.x * TILE;
+    const uint4 *ptr = reinterpret_cast<const uint4 *>(A.text) + A.group_begin + (uint64_t)blockIdx.x * TILE + tid;
+    uint32_t rel = blockIdx.x * TILE + tid;
+
+    // Two register buffers in ping-pong (no copies): while buffer A is filtered, buffer B's vectors are in flight.
+    // Order per phase: touch the current buffer (the scoreboard wait happens here), THEN issue the other buffer's
+    // loads, then filter — a wait issued after new loads would wait for those as well.
+    // HBM latency is taken off the register buffers by a bulk L2 prefetch issued by one thread per CTA, PF tiles
+    // ahead: the vector loads below then only have to cover an L2 hit.
+    constexpr uint32_t PF = 4;
+    const uint4 *cta_ptr = ptr - tid;
+    auto prefetch_tile = [&](uint32_t i) {
+        if (tid == 0 && i < n_it)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(cta_ptr + (size_t)i * rel_step), "r"(TILE * 16u) : "memory");
+    };
+    for (uint32_t i = 0; i < PF; i++) prefetch_tile(i);
+    uint4 va[UNROLL], vb[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; u++) vn[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (g0 + tile <= A.group_end)
+    for (int u = 0; u < UNROLL; u++) va[u] = vb[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (n_it)
     {
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) vn[u] = ld_vec_ordered(t4 + g0 + (uint64_t)u * THREADS + threadIdx.x);
+        for (int u = 0; u < UNROLL; u++) va[u] = ld_vec_ordered(ptr + (uint32_t)u * THREADS);
     }
-    for (; g0 + tile <= A.group_end; g0 += stride)
+    for (uint32_t it = 0; it < n_it; it += 2)
     {
-        uint4 v[UNROLL];
+        prefetch_tile(it + PF);
+        prefetch_tile(it + PF + 1);
+        touch(va);
+        if (it + 1 < n_it)
+        {
 #pragma unroll
+            for (int u = 0; u < UNROLL; u++) vb[u] = ld_vec_ordered(ptr + rel_step + (uint32_t)u * THREADS);
+        }
+        filter_push(va, rel);
+        if (it + 1 < n_it)
+        {
+            touch(vb);
+            if (it + 2 < n_it)
+            {
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) va[u] = ld_vec_ordered(ptr + 2 * (size_t)rel_step + (uint32_t)u * THREADS);
+            }
+            filter_push(vb, rel + rel_step);
+        }
+        ptr += 2 * (size_t)rel_step;
+        rel += 2 * rel_step;
+    }
+    (void)cta_ptr;
+    // ragged remainder (< one tile), handled by the CTA whose turn it would be; lanes past the end report no hit
+    if (full_tiles % gridDim.x == blockIdx.x && full_tiles * TILE < n_groups)
+    {
+        const uint4 *t4 = reinterpret_cast<const uint4 *>(A.text) + A.group_begin;
         for (int u = 0; u < UNROLL; u++)
         {
-            v[u] = vn[u];
-            asm volatile("" ::"r"(v[u].x), "r"(v[u].y), "r"(v[u].z), "r"(v[u].w));
-        }
-        const uint64_t gn = g0 + stride;
-        if (gn + tile <= A.group_end)
-        {
-#pragma unroll
-            for (int u = 0; u < UNROLL; u++) vn[u] = ld_vec_ordered(t4 + gn + (uint64_t)u * THREADS + threadIdx.x);
-        }
-        uint32_t hit[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) hit[u] = tri4_filter<FOLD>(s_base, v[u], fold, m1, nbytes, c8);
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) push(hit[u], g0 + (uint64_t)u * THREADS + threadIdx.x);
-    }
-    if (g0 < A.group_end) // ragged tile: lanes past the end re-read the last group and report no hit
-    {
-        for (int u = 0; u < UNROLL; u++)
-        {
-            const uint64_t g = g0 + (uint64_t)u * THREADS + threadIdx.x;
-            const uint64_t gc = g < A.group_end ? g : A.group_end - 1;
-            const uint32_t hit = tri4_filter<FOLD>(s_base, __ldg(t4 + gc), fold, m1, nbytes, c8);
-            push(g < A.group_end ? hit : 0u, g);
+            const uint32_t r = full_tiles * TILE + (uint32_t)u * THREADS + tid;
+            const uint32_t rc = r < n_groups ? r : n_groups - 1;
+            const uint32_t hit = tri4_filter<FOLD>(s_base, __ldg(t4 + rc), fold, m1, nbytes, c8);
+            push(r < n_groups ? hit : 0u, r);
+            drain(32);
         }
     }
-    __syncwarp();
-    if (qn) local_cnt += tri4_verify_groups<FOLD>(A, s_base, lane < qn ? s_q[lane] : 0, lane < qn);
+    drain(1);
     // tail: occurrences whose aligned window position lies beyond the last full group — brute force, lanes over patterns
-    if (blockIdx.x == 0 && threadIdx.x < 32)
+    if (A.zero == 0 && blockIdx.x == 0 && tid < 32)
     {
         const uint64_t first = A.tail_a >= 3 ? A.tail_a - 3 : 0;
         for (uint64_t p = first; p < A.avail_len; p++)
         {
             const uint64_t a = (p + 3) / 4 * 4;
             if (a < A.tail_a) continue;
-            for (uint32_t k = threadIdx.x; k < A.npat; k += 32) local_cnt += ac_verify_emit(A, k, (long long)p);
+            for (uint32_t k = tid; k < A.npat; k += 32) local_cnt += ac_verify_emit(A, k, (long long)p);
         }
     }
     if (!A.want_positions)
@@ -847,6 +942,17 @@ int ac_build_tables(Plan *plan)
         i = j;
     }
     for (auto &tb : tri_bits) bitmap[(uint32_t)(((uint64_t)(tb.first * T->mul_lo) * nby) >> 32) >> 2] |= tb.second;
+    if (tri4)
+    {
+        std::vector<uint8_t> b2(1u << 20, 0); // bit index = top 23 bits of prefix_hash
+        for (auto &e : ents)
+        {
+            const uint32_t hsh = (uint32_t)e.key * HC1 + (uint32_t)(e.key >> 32) * HC2;
+            b2[hsh >> 12] |= (uint8_t)(1u << ((hsh >> 9) & 7u));
+        }
+        CKB(cudaMalloc(&T->d_bitmap2, b2.size()));
+        CKB(cudaMemcpy(T->d_bitmap2, b2.data(), b2.size(), cudaMemcpyHostToDevice));
+    }
     if (pv.empty()) { pv.push_back(0); pm.push_back(0); }
     if (list.empty()) list.push_back(0);
     CKB(cudaMalloc(&T->d_bitmap, bitmap.size() * 4));
@@ -878,6 +984,7 @@ void ac_free_tables(Plan *plan)
     AcDevTables *T = plan->ac;
     if (!T) return;
     cudaFree(T->d_bitmap);
+    cudaFree(T->d_bitmap2);
     cudaFree(T->d_slots);
     cudaFree(T->d_list);
     cudaFree(T->d_pool_val);
@@ -894,6 +1001,7 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     AcDev A;
     memset(&A, 0, sizeof A);
     A.bitmap = T->d_bitmap;
+    A.bitmap2 = T->d_bitmap2;
     A.slots = T->d_slots;
     A.list = T->d_list;
     A.pool_val = T->d_pool_val;
@@ -940,23 +1048,43 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     }
     if (T->tri4)
     {
-        constexpr int THREADS = 768, UNROLL = 4;
+        constexpr int UNROLL = 4;
+        static int threads = 0; // CTA size: 640 (96 registers: no spills); KREP_B200_AC_THREADS=768 for experiments
+        if (!threads)
+        {
+            const char *e = getenv("KREP_B200_AC_THREADS");
+            threads = e ? atoi(e) : 640;
+            if (threads != 640 && threads != 768) threads = 640;
+        }
         const uint64_t full_groups = a.avail_len / 16; // a lookup only needs its own aligned word
         A.tail_a = full_groups * 16;
         A.group_begin = a.own_begin / 16;
         A.group_end = (a.own_end + 3) / 16 + 1; // aligned window position of an owned start lies < own_end + 4
         if (A.group_end > full_groups) A.group_end = full_groups;
         if (A.group_begin > A.group_end) A.group_begin = A.group_end;
-        const size_t smem = (size_t)T->bitmap_bytes + (size_t)(THREADS / 32) * 64 * sizeof(uint64_t);
-        auto kernel = T->fold != 0xFFFFFFFFu ? k_ac_tri4<true, THREADS, UNROLL> : k_ac_tri4<false, THREADS, UNROLL>;
+        const size_t smem = (size_t)T->bitmap_bytes + (size_t)(threads / 32) * (32 * UNROLL + 32) * sizeof(uint64_t);
+        const bool f = T->fold != 0xFFFFFFFFu;
+        void (*kernel)(AcDev) = nullptr;
+        if (threads == 640) kernel = f ? k_ac_tri4<true, 640, UNROLL> : k_ac_tri4<false, 640, UNROLL>;
+        else kernel = f ? k_ac_tri4<true, 768, UNROLL> : k_ac_tri4<false, 768, UNROLL>;
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const uint64_t groups = A.group_end - A.group_begin;
-        const uint64_t tile = (uint64_t)THREADS * UNROLL;
-        uint64_t blocks = (groups + tile - 1) / tile;
-        if (blocks == 0) blocks = 1;
-        if (blocks > (uint64_t)sm_count) blocks = sm_count;
-        kernel<<<(unsigned)blocks, THREADS, smem, st>>>(A);
-        count_launch();
+        // queue entries hold 32-bit relative group indices: at most 2^31 groups (32 GiB) per launch
+        const uint64_t gb = A.group_begin, ge = A.group_end, max_groups = 1ull << 31;
+        const uint64_t tile = (uint64_t)threads * UNROLL;
+        uint64_t b0 = gb;
+        do
+        {
+            const uint64_t e0 = ge - b0 > max_groups ? b0 + max_groups : ge;
+            A.group_begin = b0;
+            A.group_end = e0;
+            A.zero = b0 == gb ? 0u : 1u; // the first launch also scans the tail bytes
+            uint64_t blocks = (e0 - b0 + tile - 1) / tile;
+            if (blocks == 0) blocks = 1;
+            if (blocks > (uint64_t)sm_count) blocks = sm_count;
+            kernel<<<(unsigned)blocks, threads, smem, st>>>(A);
+            count_launch();
+            b0 = e0;
+        } while (b0 < ge);
         return;
     }
     constexpr int THREADS = 640, UNROLL = 4;
