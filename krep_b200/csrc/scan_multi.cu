@@ -70,6 +70,7 @@ struct AcDev
     unsigned long long *counter;
     uint32_t whole_word, want_positions;
     uint32_t zero; // always 0; opaque to the compiler (see the software pipeline in k_ac_scan)
+    uint32_t pf_dist, pf_mode; // tri4: L2 prefetch distance in tiles (0 = off); 0 = one bulk prefetch per CTA tile, 1 = per warp vector
 };
 
 static constexpr uint32_t HC1 = 0x9E3779B1u, HC2 = 0x85EBCA77u;
@@ -637,11 +638,12 @@ __device__ __forceinline__ unsigned tri4_verify_batch(const AcDev &A, uint32_t s
     return n;
 }
 
-template <bool FOLD, int THREADS, int UNROLL>
+template <bool FOLD, int THREADS, int NBUF>
 __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ AcDev A)
 {
     extern __shared__ __align__(16) uint8_t s_mem[];
-    constexpr int QCAP = 32 * UNROLL + 32; // < 32 left over + at most 32 new per vector of the batch
+    constexpr int UNROLL = 4;
+    constexpr int QCAP = 96; // < 32 left over + at most 64 new between two drains (two vectors)
     constexpr uint32_t TILE = (uint32_t)THREADS * UNROLL;
     const uint32_t nbytes = A.bitmap_bytes;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -680,17 +682,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
             local_cnt += tri4_verify_batch<FOLD>(A, s_base, e, valid, s_q, qn, lt_mask);
         }
     };
-    auto filter_push = [&](const uint4 (&v)[UNROLL], uint32_t rel0) {
-        uint32_t hm = 0; // bit u: vector u holds a passed lookup
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) hm |= tri4_filter<FOLD>(s_base, v[u], fold, m1, nbytes, c8) << u;
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) push((hm >> u) & 1u, rel0 + (uint32_t)u * THREADS);
+    auto filter_push = [&](const uint4 &v0, const uint4 &v1, const uint4 &v2, const uint4 &v3, uint32_t rel0) {
+        uint32_t hm = tri4_filter<FOLD>(s_base, v0, fold, m1, nbytes, c8);
+        hm |= tri4_filter<FOLD>(s_base, v1, fold, m1, nbytes, c8) << 1;
+        hm |= tri4_filter<FOLD>(s_base, v2, fold, m1, nbytes, c8) << 2;
+        hm |= tri4_filter<FOLD>(s_base, v3, fold, m1, nbytes, c8) << 3;
+        push(hm & 1u, rel0);
+        push((hm >> 1) & 1u, rel0 + THREADS);
+        drain(32);
+        push((hm >> 2) & 1u, rel0 + 2 * THREADS);
+        push((hm >> 3) & 1u, rel0 + 3 * THREADS);
         drain(32);
     };
-    auto touch = [](const uint4 (&v)[UNROLL]) {
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) asm volatile("" ::"r"(v[u].x), "r"(v[u].y), "r"(v[u].z), "r"(v[u].w));
+    auto touch = [](const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d) {
+        asm volatile("" ::"r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w));
+        asm volatile("" ::"r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w), "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w));
     };
 
     // This CTA owns the full tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; n_groups < 2^32 per launch (host splits).
@@ -701,51 +707,77 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
     const uint4 *ptr = reinterpret_cast<const uint4 *>(A.text) + A.group_begin + (uint64_t)blockIdx.x * TILE + tid;
     uint32_t rel = blockIdx.x * TILE + tid;
 
-    // Two register buffers in ping-pong (no copies): while buffer A is filtered, buffer B's vectors are in flight.
-    // Order per phase: touch the current buffer (the scoreboard wait happens here), THEN issue the other buffer's
-    // loads, then filter — a wait issued after new loads would wait for those as well.
-    // HBM latency is taken off the register buffers by a bulk L2 prefetch issued by one thread per CTA, PF tiles
-    // ahead: the vector loads below then only have to cover an L2 hit.
-    constexpr uint32_t PF = 4;
+    // HBM latency is taken off the registers by a bulk L2 prefetch issued by one thread per CTA, PF tiles ahead: the
+    // vector loads below only have to cover an L2 hit — with enough warps (NBUF = 1: one register buffer, 64
+    // registers, 1024 threads) or with a second register buffer in ping-pong (NBUF = 2, 96 registers, 640 threads).
+    const uint32_t PF = A.pf_dist;
     const uint4 *cta_ptr = ptr - tid;
     auto prefetch_tile = [&](uint32_t i) {
-        if (tid == 0 && i < n_it)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(cta_ptr + (size_t)i * rel_step), "r"(TILE * 16u) : "memory");
+        if (PF == 0 || i >= n_it) return;
+        if (A.pf_mode == 0)
+        {
+            if (tid == 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(cta_ptr + (size_t)i * rel_step), "r"(TILE * 16u) : "memory");
+        }
+        else if (lane == 0)
+        {
+            const uint4 *q = cta_ptr + (size_t)i * rel_step + warp * 32;
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q + u * THREADS), "r"(512u) : "memory");
+        }
     };
     for (uint32_t i = 0; i < PF; i++) prefetch_tile(i);
-    uint4 va[UNROLL], vb[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) va[u] = vb[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (n_it)
+    if constexpr (NBUF == 1)
     {
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) va[u] = ld_vec_ordered(ptr + (uint32_t)u * THREADS);
-    }
-    for (uint32_t it = 0; it < n_it; it += 2)
-    {
-        prefetch_tile(it + PF);
-        prefetch_tile(it + PF + 1);
-        touch(va);
-        if (it + 1 < n_it)
+        for (uint32_t it = 0; it < n_it; it++)
         {
-#pragma unroll
-            for (int u = 0; u < UNROLL; u++) vb[u] = ld_vec_ordered(ptr + rel_step + (uint32_t)u * THREADS);
+            prefetch_tile(it + PF);
+            const uint4 a0 = ld_vec_ordered(ptr), a1 = ld_vec_ordered(ptr + THREADS), a2 = ld_vec_ordered(ptr + 2 * THREADS),
+                        a3 = ld_vec_ordered(ptr + 3 * THREADS);
+            filter_push(a0, a1, a2, a3, rel);
+            ptr += rel_step;
+            rel += rel_step;
         }
-        filter_push(va, rel);
-        if (it + 1 < n_it)
+    }
+    else
+    {
+        // Two register buffers in ping-pong (no copies).  Order per phase: touch the current buffer (the scoreboard
+        // wait happens here), THEN issue the other buffer's loads, then filter.
+        uint4 a0, a1, a2, a3, b0, b1, b2, b3;
+        a0 = a1 = a2 = a3 = b0 = b1 = b2 = b3 = make_uint4(0u, 0u, 0u, 0u);
+        if (n_it)
         {
-            touch(vb);
-            if (it + 2 < n_it)
+            a0 = ld_vec_ordered(ptr); a1 = ld_vec_ordered(ptr + THREADS); a2 = ld_vec_ordered(ptr + 2 * THREADS);
+            a3 = ld_vec_ordered(ptr + 3 * THREADS);
+        }
+        for (uint32_t it = 0; it < n_it; it += 2)
+        {
+            prefetch_tile(it + PF);
+            prefetch_tile(it + PF + 1);
+            touch(a0, a1, a2, a3);
+            if (it + 1 < n_it)
             {
-#pragma unroll
-                for (int u = 0; u < UNROLL; u++) va[u] = ld_vec_ordered(ptr + 2 * (size_t)rel_step + (uint32_t)u * THREADS);
+                const uint4 *q = ptr + rel_step;
+                b0 = ld_vec_ordered(q); b1 = ld_vec_ordered(q + THREADS); b2 = ld_vec_ordered(q + 2 * THREADS);
+                b3 = ld_vec_ordered(q + 3 * THREADS);
             }
-            filter_push(vb, rel + rel_step);
+            filter_push(a0, a1, a2, a3, rel);
+            if (it + 1 < n_it)
+            {
+                touch(b0, b1, b2, b3);
+                if (it + 2 < n_it)
+                {
+                    const uint4 *q = ptr + 2 * (size_t)rel_step;
+                    a0 = ld_vec_ordered(q); a1 = ld_vec_ordered(q + THREADS); a2 = ld_vec_ordered(q + 2 * THREADS);
+                    a3 = ld_vec_ordered(q + 3 * THREADS);
+                }
+                filter_push(b0, b1, b2, b3, rel + rel_step);
+            }
+            ptr += 2 * (size_t)rel_step;
+            rel += 2 * rel_step;
         }
-        ptr += 2 * (size_t)rel_step;
-        rel += 2 * rel_step;
     }
-    (void)cta_ptr;
     // ragged remainder (< one tile), handled by the CTA whose turn it would be; lanes past the end report no hit
     if (full_tiles % gridDim.x == blockIdx.x && full_tiles * TILE < n_groups)
     {
@@ -1049,24 +1081,31 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     if (T->tri4)
     {
         constexpr int UNROLL = 4;
-        static int threads = 0; // CTA size: 640 (96 registers: no spills); KREP_B200_AC_THREADS=768 for experiments
+        // CTA shape: KREP_B200_AC_SHAPE = "640x2" (default) | "768x1" | "1024x1" (threads x register buffers)
+        static int threads = 0, nbuf = 0, pf_dist = 4, pf_mode = 1;
         if (!threads)
         {
-            const char *e = getenv("KREP_B200_AC_THREADS");
-            threads = e ? atoi(e) : 640;
-            if (threads != 640 && threads != 768) threads = 640;
+            if (const char *v = getenv("KREP_B200_AC_PF")) pf_dist = atoi(v);
+            if (const char *v = getenv("KREP_B200_AC_PFMODE")) pf_mode = atoi(v);
+            const char *e = getenv("KREP_B200_AC_SHAPE");
+            threads = 640; nbuf = 2;
+            if (e && !strcmp(e, "768x1")) { threads = 768; nbuf = 1; }
+            if (e && !strcmp(e, "1024x1")) { threads = 1024; nbuf = 1; }
         }
+        A.pf_dist = (uint32_t)pf_dist;
+        A.pf_mode = (uint32_t)pf_mode;
         const uint64_t full_groups = a.avail_len / 16; // a lookup only needs its own aligned word
         A.tail_a = full_groups * 16;
         A.group_begin = a.own_begin / 16;
         A.group_end = (a.own_end + 3) / 16 + 1; // aligned window position of an owned start lies < own_end + 4
         if (A.group_end > full_groups) A.group_end = full_groups;
         if (A.group_begin > A.group_end) A.group_begin = A.group_end;
-        const size_t smem = (size_t)T->bitmap_bytes + (size_t)(threads / 32) * (32 * UNROLL + 32) * sizeof(uint64_t);
+        const size_t smem = (size_t)T->bitmap_bytes + (size_t)(threads / 32) * 96 * sizeof(uint64_t);
         const bool f = T->fold != 0xFFFFFFFFu;
         void (*kernel)(AcDev) = nullptr;
-        if (threads == 640) kernel = f ? k_ac_tri4<true, 640, UNROLL> : k_ac_tri4<false, 640, UNROLL>;
-        else kernel = f ? k_ac_tri4<true, 768, UNROLL> : k_ac_tri4<false, 768, UNROLL>;
+        if (threads == 640) kernel = f ? k_ac_tri4<true, 640, 2> : k_ac_tri4<false, 640, 2>;
+        else if (threads == 768) kernel = f ? k_ac_tri4<true, 768, 1> : k_ac_tri4<false, 768, 1>;
+        else kernel = f ? k_ac_tri4<true, 1024, 1> : k_ac_tri4<false, 1024, 1>;
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         // queue entries hold 32-bit relative group indices: at most 2^31 groups (32 GiB) per launch
         const uint64_t gb = A.group_begin, ge = A.group_end, max_groups = 1ull << 31;
