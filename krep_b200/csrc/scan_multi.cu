@@ -532,29 +532,41 @@ __device__ __forceinline__ uint32_t tri4_filter(uint32_t s_base, const uint4 &v,
 
 __device__ __forceinline__ uint32_t prefix_hash(uint32_t lo, uint32_t hi) { return lo * HC1 + hi * HC2; }
 
-// Queue entry: (group index relative to group_begin) << 4 | mask of the lookups still to verify (0 = not known yet).
+// Queue entry (32 bytes of shared memory, one candidate group):
+//     [0,8)   meta = rel << 6 | next_partial << 5 | 0 << 4 | mask       rel  = group index relative to group_begin
+//                                                                         mask = lookups still to verify (0 = unknown)
+//     [8,12)  the 4 bytes before the group     [12,16) the 4 bytes after it      [16,32) the group itself
+// The group comes from the pushing lane's registers; the two neighbour words are fetched by cp.async straight into the
+// entry (no register, no stall at push time), so verification never goes back to global memory for text.
 // One entry per lane.  Every lane verifies ONE passed lookup per call; a group with more than one puts the rest back
-// into the queue, so a batch costs two L2 round trips (the 24 bytes around the group, then the four prefix probes).
-// Inlined into the scan kernel at its single drain site: a call would force the prefetched vectors of the streaming
-// loop through the ABI's few callee-saved registers, i.e. into local memory on every iteration.
+// into the queue, so a batch costs one L2 round trip (the four prefix probes).
+// Inlined into the scan kernel at its drain sites: a call would force the prefetched vectors of the streaming loop
+// through the ABI's few callee-saved registers, i.e. into local memory on every iteration.
+static constexpr uint32_t TRI4_ENTRY = 32, TRI4_QCAP = 64;
+
 template <bool FOLD>
-__device__ __forceinline__ unsigned tri4_verify_batch(const AcDev &A, uint32_t s_base, uint64_t entry, bool valid, uint64_t *s_q,
+__device__ __forceinline__ unsigned tri4_verify_batch(const AcDev &A, uint32_t s_base, uint32_t q_base, uint32_t slot, bool valid,
                                                        uint32_t &qn, uint32_t lt_mask)
 {
     unsigned n = 0;
     uint32_t X[6] = {0, 0, 0, 0, 0, 0}; // bytes [16g-4, 16g+20): previous word, the group, next word
-    uint32_t km = (uint32_t)entry & 15u;
-    const uint64_t g = A.group_begin + (entry >> 4);
+    uint32_t meta_lo = 0, meta_hi = 0;
     if (valid)
     {
-        const uint4 *t4 = reinterpret_cast<const uint4 *>(A.text);
-        const uint4 v = __ldg(t4 + g);
-        X[0] = g > 0 ? __ldg(reinterpret_cast<const uint32_t *>(t4 + g) - 1) : 0u;
-        const uint64_t nb = (g + 1) * 16;
-        if (nb + 4 <= A.avail_len) X[5] = __ldg(reinterpret_cast<const uint32_t *>(t4 + g + 1));
-        else
+        const uint32_t e = q_base + slot * TRI4_ENTRY;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(meta_lo), "=r"(meta_hi), "=r"(X[0]), "=r"(X[5]) : "r"(e));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(X[1]), "=r"(X[2]), "=r"(X[3]), "=r"(X[4]) : "r"(e + 16));
+    }
+    uint32_t km = meta_lo & 15u;
+    const uint64_t g = A.group_begin + ((((uint64_t)meta_hi << 32) | meta_lo) >> 6);
+    if (valid)
+    {
+        if (meta_lo & 32u) // the 4 bytes after the group are not all readable (last full group of the text): byte loads
+        {
+            const uint64_t nb = (g + 1) * 16;
+            X[5] = 0;
             for (uint64_t i = nb; i < A.avail_len; i++) X[5] |= (uint32_t)A.text[i] << (8 * (i - nb));
-        X[1] = v.x; X[2] = v.y; X[3] = v.z; X[4] = v.w;
+        }
         if (FOLD)
         {
 #pragma unroll
@@ -575,11 +587,17 @@ __device__ __forceinline__ unsigned tri4_verify_batch(const AcDev &A, uint32_t s
     const bool work = km != 0;
     km &= km - 1;
     {
-        // lookups beyond the first go back into the queue (room is guaranteed: this batch just left it)
+        // lookups beyond the first go back into the queue (room is guaranteed: this batch just left it); the entry is
+        // re-written from the registers it was read into (FOLD was applied: folding is idempotent)
         const uint32_t b = __ballot_sync(0xffffffffu, km != 0);
         if (b)
         {
-            if (km) s_q[qn + __popc(b & lt_mask)] = (entry & ~15ull) | km;
+            if (km)
+            {
+                const uint32_t e = q_base + (qn + __popc(b & lt_mask)) * TRI4_ENTRY;
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(e), "r"((meta_lo & ~15u) | km), "r"(meta_hi), "r"(X[0]), "r"(X[5]));
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(e + 16), "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]));
+            }
             qn += __popc(b);
         }
     }
@@ -643,11 +661,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
 {
     extern __shared__ __align__(16) uint8_t s_mem[];
     constexpr int UNROLL = 4;
-    constexpr int QCAP = 96; // < 32 left over + at most 64 new between two drains (two vectors)
     constexpr uint32_t TILE = (uint32_t)THREADS * UNROLL;
     const uint32_t nbytes = A.bitmap_bytes;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint64_t *s_q = reinterpret_cast<uint64_t *>(s_mem + nbytes) + warp * QCAP;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(A.bitmap);
         uint4 *dst = reinterpret_cast<uint4 *>(s_mem);
@@ -655,44 +671,58 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
     }
     __syncthreads();
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_mem);
+    const uint32_t q_base = s_base + nbytes + warp * (TRI4_QCAP * TRI4_ENTRY); // this warp's candidate queue
     const uint32_t fold = A.fold, m1 = A.mul_lo, c8 = A.mul_hi; // c8 = 2^8: umulhi(w, 2^8) = w >> 24 on the FMA pipe
     const uint32_t lt_mask = (1u << lane) - 1u;
     unsigned long long local_cnt = 0;
     uint32_t qn = 0; // entries in this warp's queue (warp-uniform, lives in a register)
+    const uint8_t *const text0 = A.text + A.group_begin * 16; // byte address of relative group 0
 
-    // warp-aggregated push of one candidate group per hitting lane (rel = group index relative to group_begin)
-    auto push = [&](uint32_t hit, uint32_t rel) {
-        const uint32_t b = __ballot_sync(0xffffffffu, hit != 0);
-        if (b)
-        {
-            if (hit) s_q[qn + __popc(b & lt_mask)] = (uint64_t)rel << 4;
-            qn += __popc(b);
-        }
-    };
     // verify queued candidates 32 at a time while at least `threshold` are waiting (32 in the loop, 1 at the end)
     auto drain = [&](uint32_t threshold) {
         while (qn >= threshold)
         {
-            __syncwarp();
+            asm volatile("cp.async.wait_all;" ::: "memory"); // this lane's neighbour-word copies have landed ...
+            __syncwarp();                                     // ... and so have everybody else's
             const uint32_t take = qn < 32 ? qn : 32;
             qn -= take;
-            const bool valid = lane < take;
-            const uint64_t e = valid ? s_q[qn + lane] : 0;
+            local_cnt += tri4_verify_batch<FOLD>(A, s_base, q_base, qn + lane, lane < take, qn, lt_mask);
             __syncwarp();
-            local_cnt += tri4_verify_batch<FOLD>(A, s_base, e, valid, s_q, qn, lt_mask);
         }
     };
-    auto filter_push = [&](const uint4 &v0, const uint4 &v1, const uint4 &v2, const uint4 &v3, uint32_t rel0) {
+    // One warp-aggregated push per round: every lane with a passed lookup queues the lowest of its (up to 4) groups;
+    // almost always a single round per batch of four vectors.
+    auto filter_push = [&](const uint4 &v0, const uint4 &v1, const uint4 &v2, const uint4 &v3, uint32_t rel0, uint32_t valid_mask) {
         uint32_t hm = tri4_filter<FOLD>(s_base, v0, fold, m1, nbytes, c8);
         hm |= tri4_filter<FOLD>(s_base, v1, fold, m1, nbytes, c8) << 1;
         hm |= tri4_filter<FOLD>(s_base, v2, fold, m1, nbytes, c8) << 2;
         hm |= tri4_filter<FOLD>(s_base, v3, fold, m1, nbytes, c8) << 3;
-        push(hm & 1u, rel0);
-        push((hm >> 1) & 1u, rel0 + THREADS);
-        drain(32);
-        push((hm >> 2) & 1u, rel0 + 2 * THREADS);
-        push((hm >> 3) & 1u, rel0 + 3 * THREADS);
-        drain(32);
+        hm &= valid_mask;
+        for (;;)
+        {
+            const uint32_t b = __ballot_sync(0xffffffffu, hm != 0);
+            if (b == 0) break;
+            if (hm)
+            {
+                const uint32_t u = __ffs(hm) - 1;
+                hm &= hm - 1;
+                uint4 vv = v0;
+                if (u == 1) vv = v1;
+                if (u == 2) vv = v2;
+                if (u == 3) vv = v3;
+                const uint32_t rel = rel0 + u * THREADS;
+                const uint32_t e = q_base + (qn + __popc(b & lt_mask)) * TRI4_ENTRY;
+                const uint8_t *gp = text0 + (size_t)rel * 16;
+                const bool has_prev = gp != A.text, next_ok = (uint64_t)(gp - A.text) + 20 <= A.avail_len;
+                asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(e), "r"((rel << 6) | (next_ok ? 0u : 32u)), "r"(rel >> 26));
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(e + 16), "r"(vv.x), "r"(vv.y), "r"(vv.z), "r"(vv.w));
+                if (has_prev) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(e + 8), "l"(gp - 4) : "memory");
+                else asm volatile("st.shared.u32 [%0], %1;" ::"r"(e + 8), "r"(0u));
+                if (next_ok) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(e + 12), "l"(gp + 16) : "memory");
+            }
+            qn += __popc(b);
+            drain(32);
+        }
     };
     auto touch = [](const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d) {
         asm volatile("" ::"r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w));
@@ -704,14 +734,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
     const uint32_t full_tiles = n_groups / TILE;
     const uint32_t n_it = full_tiles > blockIdx.x ? (full_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const uint32_t rel_step = gridDim.x * TILE;
-    const uint4 *ptr = reinterpret_cast<const uint4 *>(A.text) + A.group_begin + (uint64_t)blockIdx.x * TILE + tid;
-    uint32_t rel = blockIdx.x * TILE + tid;
+    uint32_t rel = blockIdx.x * TILE + tid; // the only loop-carried position: pointers are rebuilt from it
+    const uint4 *const t4rel = reinterpret_cast<const uint4 *>(text0);
 
     // HBM latency is taken off the registers by a bulk L2 prefetch issued by one thread per CTA, PF tiles ahead: the
     // vector loads below only have to cover an L2 hit — with enough warps (NBUF = 1: one register buffer, 64
     // registers, 1024 threads) or with a second register buffer in ping-pong (NBUF = 2, 96 registers, 640 threads).
     const uint32_t PF = A.pf_dist;
-    const uint4 *cta_ptr = ptr - tid;
+    const uint4 *cta_ptr = t4rel + (size_t)blockIdx.x * TILE;
     auto prefetch_tile = [&](uint32_t i) {
         if (PF == 0 || i >= n_it) return;
         if (A.pf_mode == 0)
@@ -727,16 +757,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q + u * THREADS), "r"(512u) : "memory");
         }
     };
+#pragma unroll 1
     for (uint32_t i = 0; i < PF; i++) prefetch_tile(i);
     if constexpr (NBUF == 1)
     {
         for (uint32_t it = 0; it < n_it; it++)
         {
             prefetch_tile(it + PF);
+            const uint4 *ptr = t4rel + rel;
             const uint4 a0 = ld_vec_ordered(ptr), a1 = ld_vec_ordered(ptr + THREADS), a2 = ld_vec_ordered(ptr + 2 * THREADS),
                         a3 = ld_vec_ordered(ptr + 3 * THREADS);
-            filter_push(a0, a1, a2, a3, rel);
-            ptr += rel_step;
+            filter_push(a0, a1, a2, a3, rel, 15u);
             rel += rel_step;
         }
     }
@@ -748,6 +779,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
         a0 = a1 = a2 = a3 = b0 = b1 = b2 = b3 = make_uint4(0u, 0u, 0u, 0u);
         if (n_it)
         {
+            const uint4 *ptr = t4rel + rel;
             a0 = ld_vec_ordered(ptr); a1 = ld_vec_ordered(ptr + THREADS); a2 = ld_vec_ordered(ptr + 2 * THREADS);
             a3 = ld_vec_ordered(ptr + 3 * THREADS);
         }
@@ -758,38 +790,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
             touch(a0, a1, a2, a3);
             if (it + 1 < n_it)
             {
-                const uint4 *q = ptr + rel_step;
+                const uint4 *q = t4rel + (rel + rel_step);
                 b0 = ld_vec_ordered(q); b1 = ld_vec_ordered(q + THREADS); b2 = ld_vec_ordered(q + 2 * THREADS);
                 b3 = ld_vec_ordered(q + 3 * THREADS);
             }
-            filter_push(a0, a1, a2, a3, rel);
+            filter_push(a0, a1, a2, a3, rel, 15u);
             if (it + 1 < n_it)
             {
                 touch(b0, b1, b2, b3);
                 if (it + 2 < n_it)
                 {
-                    const uint4 *q = ptr + 2 * (size_t)rel_step;
+                    const uint4 *q = t4rel + (rel + 2 * rel_step);
                     a0 = ld_vec_ordered(q); a1 = ld_vec_ordered(q + THREADS); a2 = ld_vec_ordered(q + 2 * THREADS);
                     a3 = ld_vec_ordered(q + 3 * THREADS);
                 }
-                filter_push(b0, b1, b2, b3, rel + rel_step);
+                filter_push(b0, b1, b2, b3, rel + rel_step, 15u);
             }
-            ptr += 2 * (size_t)rel_step;
             rel += 2 * rel_step;
         }
     }
-    // ragged remainder (< one tile), handled by the CTA whose turn it would be; lanes past the end report no hit
+    // ragged remainder (< one tile), handled by the CTA whose turn it would be; lanes past the end re-read the last
+    // group and are masked out
     if (full_tiles % gridDim.x == blockIdx.x && full_tiles * TILE < n_groups)
     {
         const uint4 *t4 = reinterpret_cast<const uint4 *>(A.text) + A.group_begin;
-        for (int u = 0; u < UNROLL; u++)
+        const uint32_t r0 = full_tiles * TILE + tid;
+        uint4 rv[4];
+        uint32_t vm = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
         {
-            const uint32_t r = full_tiles * TILE + (uint32_t)u * THREADS + tid;
-            const uint32_t rc = r < n_groups ? r : n_groups - 1;
-            const uint32_t hit = tri4_filter<FOLD>(s_base, __ldg(t4 + rc), fold, m1, nbytes, c8);
-            push(r < n_groups ? hit : 0u, r);
-            drain(32);
+            const uint32_t r = r0 + (uint32_t)u * THREADS;
+            rv[u] = __ldg(t4 + (r < n_groups ? r : n_groups - 1));
+            vm |= (r < n_groups ? 1u : 0u) << u;
         }
+        filter_push(rv[0], rv[1], rv[2], rv[3], r0, vm);
     }
     drain(1);
     // tail: occurrences whose aligned window position lies beyond the last full group — brute force, lanes over patterns
@@ -927,7 +962,7 @@ int ac_build_tables(Plan *plan)
         std::sort(tris.begin(), tris.end());
         const double ntri = (double)(std::unique(tris.begin(), tris.end()) - tris.begin());
         while (nby < (128u << 10) && ntri * 56.0 > (double)nby) nby *= 2;
-        if (nby == (128u << 10) && ntri * 56.0 > (double)nby) nby = 192u << 10;
+        if (nby == (128u << 10) && ntri * 56.0 > (double)nby) nby = 176u << 10; // + 40-48 KB of candidate queues <= 227 KB
     }
     else
     {
@@ -1081,16 +1116,16 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     if (T->tri4)
     {
         constexpr int UNROLL = 4;
-        // CTA shape: KREP_B200_AC_SHAPE = "640x2" (default) | "768x1" | "1024x1" (threads x register buffers)
+        // CTA shape: KREP_B200_AC_SHAPE = "640x1" (default) | "640x2" | "768x1" (threads x register buffers)
         static int threads = 0, nbuf = 0, pf_dist = 4, pf_mode = 1;
         if (!threads)
         {
             if (const char *v = getenv("KREP_B200_AC_PF")) pf_dist = atoi(v);
             if (const char *v = getenv("KREP_B200_AC_PFMODE")) pf_mode = atoi(v);
             const char *e = getenv("KREP_B200_AC_SHAPE");
-            threads = 640; nbuf = 2;
+            threads = 640; nbuf = 1;
             if (e && !strcmp(e, "768x1")) { threads = 768; nbuf = 1; }
-            if (e && !strcmp(e, "1024x1")) { threads = 1024; nbuf = 1; }
+            if (e && !strcmp(e, "640x2")) { threads = 640; nbuf = 2; }
         }
         A.pf_dist = (uint32_t)pf_dist;
         A.pf_mode = (uint32_t)pf_mode;
@@ -1100,12 +1135,12 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
         A.group_end = (a.own_end + 3) / 16 + 1; // aligned window position of an owned start lies < own_end + 4
         if (A.group_end > full_groups) A.group_end = full_groups;
         if (A.group_begin > A.group_end) A.group_begin = A.group_end;
-        const size_t smem = (size_t)T->bitmap_bytes + (size_t)(threads / 32) * 96 * sizeof(uint64_t);
+        const size_t smem = (size_t)T->bitmap_bytes + (size_t)(threads / 32) * TRI4_QCAP * TRI4_ENTRY;
         const bool f = T->fold != 0xFFFFFFFFu;
         void (*kernel)(AcDev) = nullptr;
-        if (threads == 640) kernel = f ? k_ac_tri4<true, 640, 2> : k_ac_tri4<false, 640, 2>;
-        else if (threads == 768) kernel = f ? k_ac_tri4<true, 768, 1> : k_ac_tri4<false, 768, 1>;
-        else kernel = f ? k_ac_tri4<true, 1024, 1> : k_ac_tri4<false, 1024, 1>;
+        if (threads == 768) kernel = f ? k_ac_tri4<true, 768, 1> : k_ac_tri4<false, 768, 1>;
+        else if (nbuf == 1) kernel = f ? k_ac_tri4<true, 640, 1> : k_ac_tri4<false, 640, 1>;
+        else kernel = f ? k_ac_tri4<true, 640, 2> : k_ac_tri4<false, 640, 2>;
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         // queue entries hold 32-bit relative group indices: at most 2^31 groups (32 GiB) per launch
         const uint64_t gb = A.group_begin, ge = A.group_end, max_groups = 1ull << 31;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Compare CTA shapes of the tri4 kernel: parity tests under each shape, bench, one ncu capture per shape.
 TAG=$1; O=gpurun_out; mkdir -p $O
-for shape in 1024x1 768x1 640x2; do
+for shape in 640x2 640x1 768x1; do
   export KREP_B200_AC_SHAPE=$shape
   timeout 300 python -m pytest tests -m gpu -x -q -k "aho or multi" > $O/${TAG}_pytest_$shape.log 2>&1; echo "$shape pytest rc=$? $(tail -1 $O/${TAG}_pytest_$shape.log)"
   timeout 300 python bench.py --workload multi1000 --steps 30 --no-cpu --no-e2e > $O/${TAG}_bench_$shape.json 2> $O/${TAG}_bench_$shape.err
