@@ -656,12 +656,11 @@ __device__ __forceinline__ unsigned tri4_verify_batch(const AcDev &A, uint32_t s
     return n;
 }
 
-template <bool FOLD, int THREADS, int NBUF>
+template <bool FOLD, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ AcDev A)
 {
     extern __shared__ __align__(16) uint8_t s_mem[];
-    constexpr int UNROLL = 4;
-    constexpr uint32_t TILE = (uint32_t)THREADS * UNROLL;
+    constexpr uint32_t TILE = (uint32_t)THREADS * 4; // groups per CTA iteration; each warp owns 128 consecutive groups of it
     const uint32_t nbytes = A.bitmap_bytes;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     {
@@ -677,12 +676,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
     unsigned long long local_cnt = 0;
     uint32_t qn = 0; // entries in this warp's queue (warp-uniform, lives in a register)
     const uint8_t *const text0 = A.text + A.group_begin * 16; // byte address of relative group 0
+    const uint4 *const t4rel = reinterpret_cast<const uint4 *>(text0);
 
     // verify queued candidates 32 at a time while at least `threshold` are waiting (32 in the loop, 1 at the end)
     auto drain = [&](uint32_t threshold) {
         while (qn >= threshold)
         {
-            asm volatile("cp.async.wait_all;" ::: "memory"); // this lane's neighbour-word copies have landed ...
+            asm volatile("cp.async.wait_all;" ::: "memory"); // this lane's copies into its entries have landed ...
             __syncwarp();                                     // ... and so have everybody else's
             const uint32_t take = qn < 32 ? qn : 32;
             qn -= take;
@@ -690,14 +690,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
             __syncwarp();
         }
     };
-    // One warp-aggregated push per round: every lane with a passed lookup queues the lowest of its (up to 4) groups;
-    // almost always a single round per batch of four vectors.
-    auto filter_push = [&](const uint4 &v0, const uint4 &v1, const uint4 &v2, const uint4 &v3, uint32_t rel0, uint32_t valid_mask) {
-        uint32_t hm = tri4_filter<FOLD>(s_base, v0, fold, m1, nbytes, c8);
-        hm |= tri4_filter<FOLD>(s_base, v1, fold, m1, nbytes, c8) << 1;
-        hm |= tri4_filter<FOLD>(s_base, v2, fold, m1, nbytes, c8) << 2;
-        hm |= tri4_filter<FOLD>(s_base, v3, fold, m1, nbytes, c8) << 3;
-        hm &= valid_mask;
+    // Queue the groups named by hm (bit u: group rel0 + 32u).  One warp-aggregated push per round — every lane with a
+    // passed lookup queues the lowest of its (up to 4) groups; almost always a single round.  The entry's 24 text bytes
+    // are copied by cp.async from L2 (the group was streamed through it a moment ago), so this needs no registers of the
+    // streaming loop and runs while the next vectors are in flight.
+    auto push_hits = [&](uint32_t hm, uint32_t rel0) {
         for (;;)
         {
             const uint32_t b = __ballot_sync(0xffffffffu, hm != 0);
@@ -706,16 +703,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
             {
                 const uint32_t u = __ffs(hm) - 1;
                 hm &= hm - 1;
-                uint4 vv = v0;
-                if (u == 1) vv = v1;
-                if (u == 2) vv = v2;
-                if (u == 3) vv = v3;
-                const uint32_t rel = rel0 + u * THREADS;
+                const uint32_t rel = rel0 + u * 32;
                 const uint32_t e = q_base + (qn + __popc(b & lt_mask)) * TRI4_ENTRY;
                 const uint8_t *gp = text0 + (size_t)rel * 16;
                 const bool has_prev = gp != A.text, next_ok = (uint64_t)(gp - A.text) + 20 <= A.avail_len;
                 asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(e), "r"((rel << 6) | (next_ok ? 0u : 32u)), "r"(rel >> 26));
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(e + 16), "r"(vv.x), "r"(vv.y), "r"(vv.z), "r"(vv.w));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(e + 16), "l"(gp) : "memory");
                 if (has_prev) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(e + 8), "l"(gp - 4) : "memory");
                 else asm volatile("st.shared.u32 [%0], %1;" ::"r"(e + 8), "r"(0u));
                 if (next_ok) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(e + 12), "l"(gp + 16) : "memory");
@@ -724,107 +717,62 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
             drain(32);
         }
     };
-    auto touch = [](const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d) {
-        asm volatile("" ::"r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w));
-        asm volatile("" ::"r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w), "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w));
+    auto filter4 = [&](const uint4 &v0, const uint4 &v1, const uint4 &v2, const uint4 &v3) -> uint32_t {
+        uint32_t hm = tri4_filter<FOLD>(s_base, v0, fold, m1, nbytes, c8);
+        hm |= tri4_filter<FOLD>(s_base, v1, fold, m1, nbytes, c8) << 1;
+        hm |= tri4_filter<FOLD>(s_base, v2, fold, m1, nbytes, c8) << 2;
+        hm |= tri4_filter<FOLD>(s_base, v3, fold, m1, nbytes, c8) << 3;
+        return hm;
     };
 
     // This CTA owns the full tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; n_groups < 2^32 per launch (host splits).
+    // Inside a tile warp w owns groups [128w, 128w+128): vector u of lane l is group 128w + 32u + l, so every vector
+    // load of a warp covers 512 contiguous bytes and a warp's share of a tile is one contiguous 2 KB piece.
     const uint32_t n_groups = (uint32_t)(A.group_end - A.group_begin);
     const uint32_t full_tiles = n_groups / TILE;
     const uint32_t n_it = full_tiles > blockIdx.x ? (full_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const uint32_t rel_step = gridDim.x * TILE;
-    uint32_t rel = blockIdx.x * TILE + tid; // the only loop-carried position: pointers are rebuilt from it
-    const uint4 *const t4rel = reinterpret_cast<const uint4 *>(text0);
+    uint32_t rel = blockIdx.x * TILE + warp * 128 + lane; // the only loop-carried position: pointers are rebuilt from it
 
-    // HBM latency is taken off the registers by a bulk L2 prefetch issued by one thread per CTA, PF tiles ahead: the
-    // vector loads below only have to cover an L2 hit — with enough warps (NBUF = 1: one register buffer, 64
-    // registers, 1024 threads) or with a second register buffer in ping-pong (NBUF = 2, 96 registers, 640 threads).
+    // HBM latency is taken off the registers by a bulk L2 prefetch (one instruction per warp and tile, PF tiles ahead);
+    // the remaining L2-hit latency of the vector loads is covered by queueing the PREVIOUS tile's passed lookups
+    // between issuing the loads and using them.
     const uint32_t PF = A.pf_dist;
-    const uint4 *cta_ptr = t4rel + (size_t)blockIdx.x * TILE;
-    auto prefetch_tile = [&](uint32_t i) {
-        if (PF == 0 || i >= n_it) return;
-        if (A.pf_mode == 0)
-        {
-            if (tid == 0)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(cta_ptr + (size_t)i * rel_step), "r"(TILE * 16u) : "memory");
-        }
-        else if (lane == 0)
-        {
-            const uint4 *q = cta_ptr + (size_t)i * rel_step + warp * 32;
-#pragma unroll
-            for (int u = 0; u < UNROLL; u++)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q + u * THREADS), "r"(512u) : "memory");
-        }
-    };
+    {
+        // prime the prefetch pipeline
+        const uint4 *q = t4rel + (blockIdx.x * TILE + warp * 128);
 #pragma unroll 1
-    for (uint32_t i = 0; i < PF; i++) prefetch_tile(i);
-    if constexpr (NBUF == 1)
-    {
-        for (uint32_t it = 0; it < n_it; it++)
-        {
-            prefetch_tile(it + PF);
-            const uint4 *ptr = t4rel + rel;
-            const uint4 a0 = ld_vec_ordered(ptr), a1 = ld_vec_ordered(ptr + THREADS), a2 = ld_vec_ordered(ptr + 2 * THREADS),
-                        a3 = ld_vec_ordered(ptr + 3 * THREADS);
-            filter_push(a0, a1, a2, a3, rel, 15u);
-            rel += rel_step;
-        }
+        for (uint32_t i = 0; i < PF && i < n_it; i++)
+            if (lane == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q + (size_t)i * rel_step), "r"(2048u) : "memory");
     }
-    else
+    uint32_t hm_prev = 0, rel_prev = 0;
+    for (uint32_t it = 0; it < n_it; it++)
     {
-        // Two register buffers in ping-pong (no copies).  Order per phase: touch the current buffer (the scoreboard
-        // wait happens here), THEN issue the other buffer's loads, then filter.
-        uint4 a0, a1, a2, a3, b0, b1, b2, b3;
-        a0 = a1 = a2 = a3 = b0 = b1 = b2 = b3 = make_uint4(0u, 0u, 0u, 0u);
-        if (n_it)
-        {
-            const uint4 *ptr = t4rel + rel;
-            a0 = ld_vec_ordered(ptr); a1 = ld_vec_ordered(ptr + THREADS); a2 = ld_vec_ordered(ptr + 2 * THREADS);
-            a3 = ld_vec_ordered(ptr + 3 * THREADS);
-        }
-        for (uint32_t it = 0; it < n_it; it += 2)
-        {
-            prefetch_tile(it + PF);
-            prefetch_tile(it + PF + 1);
-            touch(a0, a1, a2, a3);
-            if (it + 1 < n_it)
-            {
-                const uint4 *q = t4rel + (rel + rel_step);
-                b0 = ld_vec_ordered(q); b1 = ld_vec_ordered(q + THREADS); b2 = ld_vec_ordered(q + 2 * THREADS);
-                b3 = ld_vec_ordered(q + 3 * THREADS);
-            }
-            filter_push(a0, a1, a2, a3, rel, 15u);
-            if (it + 1 < n_it)
-            {
-                touch(b0, b1, b2, b3);
-                if (it + 2 < n_it)
-                {
-                    const uint4 *q = t4rel + (rel + 2 * rel_step);
-                    a0 = ld_vec_ordered(q); a1 = ld_vec_ordered(q + THREADS); a2 = ld_vec_ordered(q + 2 * THREADS);
-                    a3 = ld_vec_ordered(q + 3 * THREADS);
-                }
-                filter_push(b0, b1, b2, b3, rel + rel_step, 15u);
-            }
-            rel += 2 * rel_step;
-        }
+        const uint4 *ptr = t4rel + rel;
+        if (PF != 0 && it + PF < n_it && lane == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + (size_t)PF * rel_step), "r"(2048u) : "memory");
+        const uint4 a0 = ld_vec_ordered(ptr), a1 = ld_vec_ordered(ptr + 32), a2 = ld_vec_ordered(ptr + 64), a3 = ld_vec_ordered(ptr + 96);
+        push_hits(hm_prev, rel_prev);
+        hm_prev = filter4(a0, a1, a2, a3);
+        rel_prev = rel;
+        rel += rel_step;
     }
+    push_hits(hm_prev, rel_prev);
     // ragged remainder (< one tile), handled by the CTA whose turn it would be; lanes past the end re-read the last
     // group and are masked out
     if (full_tiles % gridDim.x == blockIdx.x && full_tiles * TILE < n_groups)
     {
-        const uint4 *t4 = reinterpret_cast<const uint4 *>(A.text) + A.group_begin;
-        const uint32_t r0 = full_tiles * TILE + tid;
+        const uint32_t r0 = full_tiles * TILE + warp * 128 + lane;
         uint4 rv[4];
         uint32_t vm = 0;
 #pragma unroll
         for (int u = 0; u < 4; u++)
         {
-            const uint32_t r = r0 + (uint32_t)u * THREADS;
-            rv[u] = __ldg(t4 + (r < n_groups ? r : n_groups - 1));
+            const uint32_t r = r0 + (uint32_t)u * 32;
+            rv[u] = __ldg(t4rel + (r < n_groups ? r : n_groups - 1));
             vm |= (r < n_groups ? 1u : 0u) << u;
         }
-        filter_push(rv[0], rv[1], rv[2], rv[3], r0, vm);
+        push_hits(filter4(rv[0], rv[1], rv[2], rv[3]) & vm, r0);
     }
     drain(1);
     // tail: occurrences whose aligned window position lies beyond the last full group — brute force, lanes over patterns
@@ -1116,19 +1064,16 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     if (T->tri4)
     {
         constexpr int UNROLL = 4;
-        // CTA shape: KREP_B200_AC_SHAPE = "640x1" (default) | "640x2" | "768x1" (threads x register buffers)
-        static int threads = 0, nbuf = 0, pf_dist = 4, pf_mode = 1;
+        // CTA size: KREP_B200_AC_THREADS = 640 (default) | 768; L2 prefetch distance: KREP_B200_AC_PF (tiles, 0 = off)
+        static int threads = 0, pf_dist = 4;
         if (!threads)
         {
             if (const char *v = getenv("KREP_B200_AC_PF")) pf_dist = atoi(v);
-            if (const char *v = getenv("KREP_B200_AC_PFMODE")) pf_mode = atoi(v);
-            const char *e = getenv("KREP_B200_AC_SHAPE");
-            threads = 640; nbuf = 1;
-            if (e && !strcmp(e, "768x1")) { threads = 768; nbuf = 1; }
-            if (e && !strcmp(e, "640x2")) { threads = 640; nbuf = 2; }
+            const char *e = getenv("KREP_B200_AC_THREADS");
+            threads = e && atoi(e) == 768 ? 768 : 640;
         }
         A.pf_dist = (uint32_t)pf_dist;
-        A.pf_mode = (uint32_t)pf_mode;
+        A.pf_mode = 1;
         const uint64_t full_groups = a.avail_len / 16; // a lookup only needs its own aligned word
         A.tail_a = full_groups * 16;
         A.group_begin = a.own_begin / 16;
@@ -1138,9 +1083,8 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
         const size_t smem = (size_t)T->bitmap_bytes + (size_t)(threads / 32) * TRI4_QCAP * TRI4_ENTRY;
         const bool f = T->fold != 0xFFFFFFFFu;
         void (*kernel)(AcDev) = nullptr;
-        if (threads == 768) kernel = f ? k_ac_tri4<true, 768, 1> : k_ac_tri4<false, 768, 1>;
-        else if (nbuf == 1) kernel = f ? k_ac_tri4<true, 640, 1> : k_ac_tri4<false, 640, 1>;
-        else kernel = f ? k_ac_tri4<true, 640, 2> : k_ac_tri4<false, 640, 2>;
+        if (threads == 768) kernel = f ? k_ac_tri4<true, 768> : k_ac_tri4<false, 768>;
+        else kernel = f ? k_ac_tri4<true, 640> : k_ac_tri4<false, 640>;
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         // queue entries hold 32-bit relative group indices: at most 2^31 groups (32 GiB) per launch
         const uint64_t gb = A.group_begin, ge = A.group_end, max_groups = 1ull << 31;
