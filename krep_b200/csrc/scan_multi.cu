@@ -47,6 +47,7 @@ struct AcDevTables
     uint32_t fold = 0xFFFFFFFFu;
     uint32_t mul_lo = 0, mul_hi = 0, mul_b = 0, bit_shift = 0;
     bool tri4 = false; // stride-4 trigram filter (Lmin == 6), see k_ac_tri4
+    uint32_t cls_mask = 0, cls_val = 0;
 };
 
 struct AcDev
@@ -70,6 +71,7 @@ struct AcDev
     unsigned long long *counter;
     uint32_t whole_word, want_positions;
     uint32_t zero; // always 0; opaque to the compiler (see the software pipeline in k_ac_scan)
+    uint32_t cls_mask, cls_val; // tri4: bits on which ALL pattern trigrams agree — a text word that differs there skips its lookup
     uint32_t pf_dist, pf_mode; // tri4: L2 prefetch distance in tiles (0 = off); 0 = one bulk prefetch per CTA tile, 1 = per warp vector
 };
 
@@ -513,9 +515,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
 // word at offset d", so each of the four starts p = a - d is tested by probing its 6 bytes [p, p+6) — four independent
 // L2 loads issued together, almost always an empty slot — and only a prefix hit goes on to the full compare.
 // =============================================================================================
+// cm / cv: the bits on which all pattern trigrams agree (e.g. 0x00E0E0E0 / 0x00606060 for lowercase-only sets).  A text
+// word that differs there cannot pass, so its lane sits the shared-memory load out: the load is a random gather whose
+// cost is its bank conflicts (~3.6 wavefronts with 32 lanes active), and the shared-memory pipe is what bounds this
+// kernel — with a third of the lanes active the same instruction takes ~1.9 wavefronts.
 template <bool FOLD>
 __device__ __forceinline__ uint32_t tri4_filter(uint32_t s_base, const uint4 &v, uint32_t fold, uint32_t m1, uint32_t nbytes,
-                                                uint32_t c8)
+                                                uint32_t c8, uint32_t cm, uint32_t cv)
 {
     uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t acc = 0;
@@ -523,8 +529,12 @@ __device__ __forceinline__ uint32_t tri4_filter(uint32_t s_base, const uint4 &v,
     for (int k = 0; k < 4; k++)
     {
         if (FOLD) w[k] &= fold;
-        const uint32_t addr = __umulhi(w[k] * m1, nbytes) & ~3u;
-        const uint32_t word = lds_u32(s_base + addr);
+        // branch-free: the lane's load is predicated off (word = 0) when the class test fails
+        const uint32_t addr = s_base + (__umulhi(w[k] * m1, nbytes) & ~3u);
+        uint32_t word;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, %3;\n\tmov.u32 %0, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
+                     : "=r"(word)
+                     : "r"(addr), "r"(w[k] & cm), "r"(cv));
         acc |= __funnelshift_r(word, 0u, __umulhi(w[k], c8));
     }
     return acc & 1u;
@@ -717,11 +727,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
             drain(32);
         }
     };
+    const uint32_t cm = A.cls_mask, cv = A.cls_val;
     auto filter4 = [&](const uint4 &v0, const uint4 &v1, const uint4 &v2, const uint4 &v3) -> uint32_t {
-        uint32_t hm = tri4_filter<FOLD>(s_base, v0, fold, m1, nbytes, c8);
-        hm |= tri4_filter<FOLD>(s_base, v1, fold, m1, nbytes, c8) << 1;
-        hm |= tri4_filter<FOLD>(s_base, v2, fold, m1, nbytes, c8) << 2;
-        hm |= tri4_filter<FOLD>(s_base, v3, fold, m1, nbytes, c8) << 3;
+        uint32_t hm = tri4_filter<FOLD>(s_base, v0, fold, m1, nbytes, c8, cm, cv);
+        hm |= tri4_filter<FOLD>(s_base, v1, fold, m1, nbytes, c8, cm, cv) << 1;
+        hm |= tri4_filter<FOLD>(s_base, v2, fold, m1, nbytes, c8, cm, cv) << 2;
+        hm |= tri4_filter<FOLD>(s_base, v3, fold, m1, nbytes, c8, cm, cv) << 3;
         return hm;
     };
 
@@ -957,6 +968,13 @@ int ac_build_tables(Plan *plan)
         i = j;
     }
     for (auto &tb : tri_bits) bitmap[(uint32_t)(((uint64_t)(tb.first * T->mul_lo) * nby) >> 32) >> 2] |= tb.second;
+    if (tri4 && !tri_bits.empty())
+    {
+        uint32_t agree = 0x00FFFFFFu;
+        for (auto &tb : tri_bits) agree &= ~(tb.first ^ tri_bits[0].first);
+        T->cls_mask = agree & 0x00FFFFFFu;
+        T->cls_val = tri_bits[0].first & T->cls_mask;
+    }
     if (tri4)
     {
         std::vector<uint8_t> b2(1u << 20, 0); // bit index = top 23 bits of prefix_hash
@@ -1034,6 +1052,8 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     A.mul_hi = T->mul_hi;
     A.bit_shift = T->bit_shift;
     A.mul_b = T->mul_b;
+    A.cls_mask = T->cls_mask;
+    A.cls_val = T->cls_val;
     A.text = a.text;
     A.avail_len = a.avail_len;
     A.own_begin = a.own_begin;
