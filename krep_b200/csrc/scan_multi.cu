@@ -532,9 +532,11 @@ __device__ __forceinline__ uint32_t tri4_filter(uint32_t s_base, const uint4 &v,
         // branch-free: the lane's load is predicated off (word = 0) when the class test fails
         const uint32_t addr = s_base + (__umulhi(w[k] * m1, nbytes) & ~3u);
         uint32_t word;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, %3;\n\tmov.u32 %0, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
+        // one LOP3 computes (w & cm) ^ cv and sets the predicate "differs" (lop3 with a predicate output)
+        asm volatile("{\n\t.reg .pred p, f;\n\t.reg .b32 t;\n\tsetp.ne.u32 f, 0, 0;\n\tlop3.or.b32 t|p, %2, %3, %4, 0x6A, f;\n\t"
+                     "mov.u32 %0, 0;\n\t@!p ld.shared.u32 %0, [%1];\n\t}"
                      : "=r"(word)
-                     : "r"(addr), "r"(w[k] & cm), "r"(cv));
+                     : "r"(addr), "r"(w[k]), "r"(cm), "r"(cv));
         acc |= __funnelshift_r(word, 0u, __umulhi(w[k], c8));
     }
     return acc & 1u;
@@ -687,6 +689,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
     uint32_t qn = 0; // entries in this warp's queue (warp-uniform, lives in a register)
     const uint8_t *const text0 = A.text + A.group_begin * 16; // byte address of relative group 0
     const uint4 *const t4rel = reinterpret_cast<const uint4 *>(text0);
+    // relative group that has no byte before it (group 0 of the buffer), and first relative group whose following
+    // 4 bytes are not all readable (16 (g + 1) + 4 > avail_len)
+    const uint32_t no_prev_rel = A.group_begin == 0 ? 0u : 0xFFFFFFFFu;
+    const uint64_t g_lim = A.avail_len >= 20 ? (A.avail_len - 20) / 16 + 1 : 0; // groups g < g_lim have a readable next word
+    const uint32_t next_ok_rel = g_lim <= A.group_begin ? 0u : (g_lim - A.group_begin > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)(g_lim - A.group_begin));
 
     // verify queued candidates 32 at a time while at least `threshold` are waiting (32 in the loop, 1 at the end)
     auto drain = [&](uint32_t threshold) {
@@ -716,7 +723,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_tri4(const __grid_constant__ 
                 const uint32_t rel = rel0 + u * 32;
                 const uint32_t e = q_base + (qn + __popc(b & lt_mask)) * TRI4_ENTRY;
                 const uint8_t *gp = text0 + (size_t)rel * 16;
-                const bool has_prev = gp != A.text, next_ok = (uint64_t)(gp - A.text) + 20 <= A.avail_len;
+                const bool has_prev = rel != no_prev_rel, next_ok = rel < next_ok_rel;
                 asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(e), "r"((rel << 6) | (next_ok ? 0u : 32u)), "r"(rel >> 26));
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(e + 16), "l"(gp) : "memory");
                 if (has_prev) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(e + 8), "l"(gp - 4) : "memory");
@@ -1084,13 +1091,13 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     if (T->tri4)
     {
         constexpr int UNROLL = 4;
-        // CTA size: KREP_B200_AC_THREADS = 640 (default) | 768; L2 prefetch distance: KREP_B200_AC_PF (tiles, 0 = off)
+        // CTA size: KREP_B200_AC_THREADS = 768 (default) | 640; L2 prefetch distance: KREP_B200_AC_PF (tiles, 0 = off)
         static int threads = 0, pf_dist = 4;
         if (!threads)
         {
             if (const char *v = getenv("KREP_B200_AC_PF")) pf_dist = atoi(v);
             const char *e = getenv("KREP_B200_AC_THREADS");
-            threads = e && atoi(e) == 768 ? 768 : 640;
+            threads = e && atoi(e) == 640 ? 640 : 768;
         }
         A.pf_dist = (uint32_t)pf_dist;
         A.pf_mode = 1;
