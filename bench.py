@@ -232,6 +232,18 @@ def run_cpu_reference(wl_name, wl, sample_bytes, steps, warmup, keep_file=False)
 
 # ------------------------------------------------------------------------------------------------
 def main():
+    # The contract is ONE JSON line on stdout: keep the real stdout aside and point fd 1 at stderr, so that nothing a
+    # native library prints (e.g. NCCL's version banner) can land in front of it.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(out_stream):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -259,14 +271,14 @@ def main():
             return
         sample = int(min(args.cpu_sample_gib, args.gib) * GIB)
         r = run_cpu_reference(args.workload, wl, sample, max(args.steps, 1), args.warmup)
-        print(json.dumps({
+        print(file=out_stream, *[json.dumps({
             "impl": "reference", "metric": metric, "value": r["value"], "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "matches_in_sample": r["count"],
-        }))
+        })])
         return
 
     import torch
@@ -308,6 +320,8 @@ def main():
     dev = DeviceResult()
     res = L.krep_b200_match_result_init(1 << 16)
 
+    gatherer = sharding.KeyGatherer(world, rank, "cuda") if world > 1 else None
+
     def step():
         rc = L.krep_b200_scan_shard(plan, C.byref(shard), 1, sptr, C.byref(dev))
         assert rc == 0, L.krep_b200_last_error_string()
@@ -316,15 +330,20 @@ def main():
             res.contents.count = 0
             total = L.krep_b200_collect(plan, params.ref(), C.byref(dev), res)
             return total, kms
-        # N>1: one gather of per-GPU counts, then of the (padded) sorted key lists, to rank 0 (krep_b200/sharding.py)
-        mine = torch.empty(max(int(dev.stored), 1), dtype=torch.int64, device="cuda")
-        L.krep_b200_export_keys(C.byref(dev), mine.data_ptr(), int(dev.stored), sptr)
-        keys, counts = sharding.gather_keys(mine[: int(dev.stored)], world, rank, "cuda")
+        # N>1: ONE collective — every rank all_gathers [count, sorted keys]; rank 0 reads the rows back and replays the
+        # concatenation (rank order = global order), krep_b200/sharding.py
+        while True:
+            n_mine = int(dev.stored)
+            if n_mine <= gatherer.cap:
+                L.krep_b200_export_keys(C.byref(dev), gatherer.key_buffer().data_ptr(), n_mine, sptr)
+            keys, counts, retry = gatherer.exchange(n_mine)
+            if not retry:
+                break
         total = 0
         if rank == 0:
             res.contents.count = 0
             arr = C.cast(keys.data_ptr(), C.POINTER(C.c_uint64))
-            total = L.krep_b200_replay(algo, params.ref(), False, arr, keys.numel(), None, 0, res)
+            total = L.krep_b200_replay(algo, params.ref(), False, arr, keys.numel(), None, world * n, res)
         return total, kms
 
     def barrier():
@@ -448,7 +467,7 @@ def main():
             out["cpu_baseline"]["matches_in_sample"] = r["count"]
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"error": str(e)}
-    print(json.dumps(out))
+    print(json.dumps(out), file=out_stream)
     if world > 1:
         dist.destroy_process_group()
 

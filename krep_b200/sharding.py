@@ -40,3 +40,45 @@ def gather_keys(local_keys, world, rank, device):
         return None, counts
     # shards are disjoint and ordered by rank, so concatenation in rank order is globally sorted
     return torch.cat([g[:c] for g, c in zip(gathered, counts)]).cpu(), counts
+
+
+class KeyGatherer:
+    """The same exchange with persistent buffers and ONE collective per step, for the benchmark's steady state:
+    every rank all_gathers a fixed-capacity row [count, key_0 .. key_{cap-1}]; rank 0 reads the rows back in one
+    device-to-host copy and concatenates the valid prefixes (rank order = global order, see gather_keys).  If any
+    rank's count exceeds the capacity every rank sees it in the gathered counts, grows its buffers to the same new
+    capacity and the step is repeated — capacity is a pure function of the gathered counts, so ranks never disagree."""
+
+    def __init__(self, world, rank, device, capacity=1 << 14):
+        self.world, self.rank, self.device = world, rank, device
+        self._alloc(capacity)
+
+    def _alloc(self, capacity):
+        self.cap = int(capacity)
+        self.row = torch.zeros(self.cap + 1, dtype=torch.int64, device=self.device)
+        self.all = torch.zeros((self.world, self.cap + 1), dtype=torch.int64, device=self.device)
+        pin = self.device != "cpu" and torch.cuda.is_available()
+        self.host = torch.zeros((self.world, self.cap + 1), dtype=torch.int64, pin_memory=pin) if self.rank == 0 else None
+        self.host_counts = torch.zeros(self.world, dtype=torch.int64, pin_memory=pin)
+
+    def key_buffer(self):
+        """Device buffer the rank's sorted keys are written into (row[1:], at most `cap` keys)."""
+        return self.row[1:]
+
+    def exchange(self, count):
+        """`count` keys are in key_buffer() (or count > cap and the caller will be told to retry).
+        -> (keys on host as a 1-D int64 tensor on rank 0 else None, counts list, retry flag)."""
+        self.row[0] = int(count)
+        dist.all_gather(list(self.all.unbind(0)), self.row)
+        self.host_counts.copy_(self.all[:, 0], non_blocking=False)
+        counts = [int(c) for c in self.host_counts.tolist()]
+        if max(counts) > self.cap:
+            cap = self.cap
+            while cap < max(counts):
+                cap *= 2
+            self._alloc(cap * 2)
+            return None, counts, True
+        if self.rank != 0:
+            return None, counts, False
+        self.host.copy_(self.all, non_blocking=False)
+        return torch.cat([self.host[r, 1:1 + c] for r, c in enumerate(counts)]), counts, False

@@ -76,6 +76,7 @@ def worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     L = lib.load()
     ok = True
+    gatherer = sharding.KeyGatherer(world, rank, "cpu", capacity=4)  # tiny: the grow-and-retry path runs too
     try:
         for ci, (func, algo, pats, opts) in enumerate(CASES):
             for n in (1000, 4099):
@@ -84,6 +85,16 @@ def worker(rank, world, port, q):
                 begin, own, avail = sharding.shard_bounds(n, world, rank, halo)
                 keys = shard_keys(func, pats, opts, text, begin, own, avail)
                 allk, counts = sharding.gather_keys(torch.tensor(keys, dtype=torch.int64), world, rank, "cpu")
+                # the single-collective exchange used by bench.py must deliver the same list
+                while True:
+                    if len(keys) <= gatherer.cap:
+                        gatherer.key_buffer()[: len(keys)] = torch.tensor(keys, dtype=torch.int64)
+                    allk2, counts2, retry = gatherer.exchange(len(keys))
+                    if not retry:
+                        break
+                if rank == 0 and (counts2 != counts or not torch.equal(allk2, allk)):
+                    ok = False
+                    q.put(("gatherer mismatch", func, n, world))
                 if rank == 0:
                     p = Params(pats, **opts)
                     if func == "aho_corasick":
