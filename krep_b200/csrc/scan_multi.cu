@@ -46,7 +46,7 @@ struct AcDevTables
     uint64_t wmask = 0; // low w bytes
     uint32_t fold = 0xFFFFFFFFu;
     uint32_t mul_lo = 0, mul_hi = 0, mul_b = 0, bit_shift = 0;
-    bool tri4 = false; // stride-4 trigram filter (Lmin == 6), see k_ac_tri4
+    bool tri4 = false; // aligned-word stride-4 filter (Lmin >= 6), see k_ac_tri4
     uint32_t cls_mask = 0, cls_val = 0;
 };
 
@@ -591,7 +591,7 @@ __device__ __forceinline__ unsigned tri4_verify_batch(const AcDev &A, uint32_t s
             {
                 const uint32_t w = X[k + 1];
                 const uint32_t word = lds_u32(s_base + (__umulhi(w * A.mul_lo, A.bitmap_bytes) & ~3u));
-                km |= ((word >> ((w >> 24) & 31u)) & 1u) << k;
+                km |= ((word >> (__umulhi(w, A.mul_hi) & 31u)) & 1u) << k;
             }
         }
     }
@@ -853,11 +853,12 @@ int ac_build_tables(Plan *plan)
     plan->min_len = lmin;
     plan->max_len = lmax;
     uint32_t w, s;
-    const bool tri4 = lmin == 6;
+    // Lmin >= 6: the aligned-word filter (k_ac_tri4).  Lmin == 6 keys it by the word's low three bytes and selects the
+    // bit with its top byte ("tri"); from Lmin = 7 on every (pattern, d) knows the whole aligned word, so the word index
+    // is a hash of all four bytes and the bit index a second hash of them ("quad") — same kernel, other constants.
+    const bool tri4 = lmin >= 6, quad = lmin >= 7;
     T->tri4 = tri4;
-    if (tri4) { w = 3; s = 4; }
-    else if (lmin >= 11) { w = 8; s = 4; }
-    else if (lmin >= 7) { w = lmin - 3; s = 4; }
+    if (tri4) { w = quad ? 4 : 3; s = 4; }
     else if (lmin >= 5) { w = lmin - 1; s = 2; }
     else { w = lmin ? lmin : 1; s = 1; }
     T->w = w;
@@ -868,10 +869,10 @@ int ac_build_tables(Plan *plan)
     T->mul_lo = w >= 4 ? HC1 : (HC1 << (8 * (4 - w)));
     T->mul_hi = w > 4 ? (w >= 8 ? HC2 : (HC2 << (8 * (8 - w)))) : 0u;
     T->bit_shift = w >= 4 ? 0u : 8 * (4 - w);
-    if (tri4) // k_ac_tri4: mul_lo drops byte 3 of the word, mul_hi = 2^8 (w >> 24 on the FMA pipe)
+    if (tri4) // k_ac_tri4: word index = umulhi(w * mul_lo, bytes), bit index = umulhi(w, mul_hi) & 31
     {
-        T->mul_lo = HC1 << 8;
-        T->mul_hi = 1u << 8;
+        T->mul_lo = quad ? HC1 : (HC1 << 8);  // tri: the zero low byte drops byte 3 of the word
+        T->mul_hi = quad ? HC2 : (1u << 8);   // tri: w >> 24 (on the FMA pipe)
         T->mul_b = 0;
     }
     if (s == 2) // paired scheme (ac_pair_filter): mT masks T to w-2 bytes, mA to 2 bytes, mB to w-2 bytes
@@ -905,6 +906,12 @@ int ac_build_tables(Plan *plan)
             ents.push_back({pat_window(pb, 6, T->fold) & 0xFFFFFFFFFFFFull, k});
             for (uint32_t d = 0; d < 4; d++)
             {
+                if (quad)
+                {
+                    const uint32_t word = (uint32_t)pat_window(pb + d, 4, T->fold);
+                    tri_bits.push_back({word, 1u << ((uint32_t)(((uint64_t)word * T->mul_hi) >> 32) & 31u)});
+                    continue;
+                }
                 const uint32_t tri = (uint32_t)pat_window(pb + d, 3, T->fold) & 0xFFFFFFu;
                 // (len, d) = (6, 3) does not know byte a+3: all 32 bits
                 tri_bits.push_back({tri, len[k] - d >= 4 ? (1u << ((pb[d + 3] & T->fold) & 31u)) : 0xFFFFFFFFu});
@@ -977,9 +984,10 @@ int ac_build_tables(Plan *plan)
     for (auto &tb : tri_bits) bitmap[(uint32_t)(((uint64_t)(tb.first * T->mul_lo) * nby) >> 32) >> 2] |= tb.second;
     if (tri4 && !tri_bits.empty())
     {
-        uint32_t agree = 0x00FFFFFFu;
+        const uint32_t span = quad ? 0xFFFFFFFFu : 0x00FFFFFFu; // bytes of the word every entry knows
+        uint32_t agree = span;
         for (auto &tb : tri_bits) agree &= ~(tb.first ^ tri_bits[0].first);
-        T->cls_mask = agree & 0x00FFFFFFu;
+        T->cls_mask = agree & span;
         T->cls_val = tri_bits[0].first & T->cls_mask;
     }
     if (tri4)
@@ -1013,7 +1021,7 @@ int ac_build_tables(Plan *plan)
         CKB(cudaMemcpy(T->d_pat_len, len.data(), K * 4, cudaMemcpyHostToDevice));
     }
     char name[96];
-    snprintf(name, sizeof name, "window%u/stride%u%s bitmap %uKB%s", w, s, tri4 ? " tri4+byte-select" : (s == 2 ? " paired" : ""), nby >> 10,
+    snprintf(name, sizeof name, "window%u/stride%u%s bitmap %uKB%s", w, s, tri4 ? (quad ? " aligned-word hash" : " tri4+byte-select") : (s == 2 ? " paired" : ""), nby >> 10,
              plan->case_sensitive ? "" : " fold");
     plan->filter_name = name;
     return 0;

@@ -126,19 +126,21 @@ def test_aho_corasick_short_and_mixed_lengths():
             assert got == want, (pats, opts)
 
 
-def test_aho_corasick_shortest_pattern_6_bytes_stride4_filter():
-    """Pattern sets whose shortest pattern has 6 bytes take the stride-4 trigram filter (k_ac_tri4): every start
-    alignment, the (len 6, d 3) entries that do not know the byte after the trigram, tails shorter than a group,
-    heavy overlap, -i and -w."""
+def test_aho_corasick_shortest_pattern_6_bytes_or_more_aligned_word_filter():
+    """Pattern sets whose shortest pattern has >= 6 bytes take the aligned-word stride-4 filter (k_ac_tri4): keyed by
+    three bytes + a selector byte when the shortest pattern has 6 bytes, by a hash of the whole word from 7 on.  Every
+    start alignment, the (len 6, d 3) entries that do not know the selector byte, tails shorter than a group, heavy
+    overlap, -i and -w."""
     rng = random.Random(66)
     chk = checker()
-    for trial in range(60):
+    for trial in range(90):
         alpha = rng.choice([b"ab", b"abc", b"abcdefgh \n", b"aAbB_ 1\n"])
+        lmin = rng.choice([6, 6, 7, 8, 11])
         n = rng.choice([6, 7, 15, 16, 17, 31, 32, 33, 47, 64, 100, 1000, 5000, 70_000])
         text = bytes(rng.choice(alpha) for _ in range(n))
         pats = []
         for _ in range(rng.randint(1, 12)):
-            m = rng.randint(6, 10)
+            m = rng.randint(lmin, lmin + 4)
             if n >= m and rng.random() < 0.8:
                 s = rng.randrange(0, n - m + 1)
                 pats.append(text[s:s + m])
@@ -146,18 +148,16 @@ def test_aho_corasick_shortest_pattern_6_bytes_stride4_filter():
                 pats.append(bytes(rng.choice(alpha) for _ in range(m)))
         if rng.random() < 0.3:
             pats.append(pats[0])
-        if rng.random() < 0.3:
-            pats[0] = pats[0][:6]
-        pats[rng.randrange(len(pats))] = (pats[0] * 2)[:6]  # at least one 6-byte pattern
+        pats[rng.randrange(len(pats))] = (pats[0] * 2)[:lmin]  # at least one pattern of the minimum length
         opts = dict(case_sensitive=rng.random() < 0.6, whole_word=rng.random() < 0.3,
                     count=rng.random() < 0.2, max_count=rng.choice([SIZE_MAX, SIZE_MAX, 1, 5]))
         got = lib.search("aho_corasick", Params(pats, **opts), text)
         want = chk.run("aho_corasick", Params(pats, **opts), text)
         assert got == want, (pats, text[:200], opts, got[0], want[0])
-    # all four alignments of a 6-byte pattern and of a longer one around group and buffer edges
+    # all four alignments of a minimum-length pattern and of a longer one around group and buffer edges
     for base in (b"x" * 64, b"q" * 61):
-        for pat in (b"needle", b"needle_7"):
+        for pat, other in ((b"needle", b"zzzzzz"), (b"needle_7", b"zzzzzz"), (b"needle_7", b"zzzzzzzz"), (b"needle_7_9", b"yyyyyyyy")):
             for off in range(0, len(base) - len(pat) + 1):
                 text = base[:off] + pat + base[off + len(pat):]
-                got = lib.search("aho_corasick", Params([pat, b"zzzzzz"]), text)
+                got = lib.search("aho_corasick", Params([pat, other]), text)
                 assert got == (1, [(off, off + len(pat))]), (pat, off, got)
