@@ -36,6 +36,11 @@ WORKLOADS = {
                    desc="-w 16-byte literal, low hit rate (BASELINE configs[4])"),
     "multi1000": dict(needle=b"kqzvxjwpy", opts={}, flags=0, period=1 << 22, multi=1000,
                       desc="1000 patterns of 6-12 bytes (-f), Aho-Corasick result set (BASELINE configs[3])"),
+    # side workloads (not BASELINE configs): other regimes of the multi-pattern filter
+    "multi1000_8to14": dict(needle=b"kqzvxjwpy", opts={}, flags=0, period=1 << 22, multi=1000, lens=(8, 14),
+                            desc="1000 patterns of 8-14 bytes (-f): shortest pattern >= 7, full-word hash filter"),
+    "multi1000_i": dict(needle=b"kqzvxjwpy", opts=dict(case_sensitive=False), flags=1, period=1 << 22, multi=1000,
+                        desc="1000 patterns of 6-12 bytes, -i"),
 }
 SEED, PLANT_SEED = 0x5EED0001, 0x5EED0002
 
@@ -48,13 +53,13 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def multi_patterns(n, needle):
+def multi_patterns(n, needle, lens=(6, 12)):
     import random
     rng = random.Random(0x5EED0003)
     alpha = "abcdefghijklmnopqrstuvwxyz"
     pats = {needle}
     while len(pats) < n:
-        pats.add("".join(rng.choice(alpha) for _ in range(rng.randint(6, 12))).encode())
+        pats.add("".join(rng.choice(alpha) for _ in range(rng.randint(*lens))).encode())
     return [needle] + sorted(pats - {needle})
 
 
@@ -81,6 +86,17 @@ class ClockSampler:
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def wait_first_sample(self, timeout=3.0):
+        """nvidia-smi needs ~100 ms before its first line: do not let a short timed region start (and end) before it."""
+        t_end = time.time() + timeout
+        while self.proc and time.time() < t_end:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.01)
 
     def mark_begin(self):
         self.t0 = time.time()
@@ -178,7 +194,7 @@ def run_cpu_reference(wl_name, wl, sample_bytes, steps, warmup, keep_file=False)
     shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     sample_path = os.path.join(shm, f"krep_b200_sample_{os.getpid()}.txt")
     pat_file = sample_path + ".pats"
-    pats = multi_patterns(wl["multi"], wl["needle"]) if wl.get("multi") else None
+    pats = multi_patterns(wl["multi"], wl["needle"], wl.get("lens", (6, 12))) if wl.get("multi") else None
 
     def spec_factory():
         return lib.make_spec(SEED, PLANT_SEED, wl["period"], wl["needle"], wl["flags"])
@@ -294,7 +310,7 @@ def _main(out_stream):
 
     n = int(args.gib * GIB)
     n -= n % 16
-    pats = multi_patterns(wl["multi"], wl["needle"]) if wl.get("multi") else None
+    pats = multi_patterns(wl["multi"], wl["needle"], wl.get("lens", (6, 12))) if wl.get("multi") else None
     maxlen = max(map(len, pats)) if pats else len(wl["needle"])
     halo = maxlen + 1
     last = rank == world - 1
@@ -357,6 +373,8 @@ def _main(out_stream):
     for _ in range(max(args.warmup, 3) if args.steps else 0):
         step()
     L.krep_b200_reset_launch_count()
+    if rank == 0:
+        sampler.wait_first_sample()
     barrier()
     sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

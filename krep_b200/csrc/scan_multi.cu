@@ -1099,13 +1099,13 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     if (T->tri4)
     {
         constexpr int UNROLL = 4;
-        // CTA size: KREP_B200_AC_THREADS = 768 (default) | 640; L2 prefetch distance: KREP_B200_AC_PF (tiles, 0 = off)
+        // CTA size: KREP_B200_AC_THREADS = 640 (default: 96 registers, no spills) | 768; L2 prefetch distance: KREP_B200_AC_PF (tiles, 0 = off)
         static int threads = 0, pf_dist = 4;
         if (!threads)
         {
             if (const char *v = getenv("KREP_B200_AC_PF")) pf_dist = atoi(v);
             const char *e = getenv("KREP_B200_AC_THREADS");
-            threads = e && atoi(e) == 640 ? 640 : 768;
+            threads = e && atoi(e) == 768 ? 768 : 640;
         }
         A.pf_dist = (uint32_t)pf_dist;
         A.pf_mode = 1;
