@@ -189,6 +189,9 @@ typedef struct
    int overflow;            /* 1 if count > capacity: call again with a larger capacity */
    uint64_t text_len;       /* global_offset + avail_len of the scanned shard: the length of the whole text when
                                the shard is the last (or only) one — what the window kernels' tail logic needs */
+   const uint64_t *d_line_bounds; /* device, 2 words per stored key, only for plans created with count_lines_mode (-c):
+                               global offset of the first byte of the occurrence's line, and of the line's newline (or
+                               the text length) — find_line_start / find_line_end (krep.c:363, 401) computed on the GPU */
 } krep_b200_device_result_t;
 
 /* Scan one shard on `stream` (cudaStream_t, NULL = engine stream): launches the
@@ -214,10 +217,12 @@ float krep_b200_last_kernel_ms(void);
 uint64_t krep_b200_launch_count(void);
 void krep_b200_reset_launch_count(void);
 
-/* Apply the emulated reference kernel's policy (overlap rule, -m cap) to a
+/* Apply the emulated reference kernel's policy (overlap rule, -w, -c, -m) to a
  * shard result and deliver it as krep's match_result_t (host, malloc memory).
- * Count-lines mode needs host text and is only available through the
- * search_func_t entry points. Returns the count the reference would return. */
+ * Count-lines mode (-c) uses the line bounds the scan computed on the device
+ * (plan created from params with count_lines_mode set, single shard: the
+ * shard must not cut a line, i.e. prev_byte = next_byte = -1 or newline-aligned).
+ * Returns the count the reference would return. */
 uint64_t krep_b200_collect(const krep_b200_plan_t *plan, const search_params_t *params,
                            const krep_b200_device_result_t *dev, match_result_t *result);
 
@@ -232,6 +237,14 @@ uint64_t krep_b200_collect(const krep_b200_plan_t *plan, const search_params_t *
 uint64_t krep_b200_replay(int algo, const search_params_t *params, bool only_matching,
                           const uint64_t *keys, uint64_t nkeys,
                           const char *text, size_t text_len, match_result_t *result);
+
+/* The same replay without any host text: `bounds` holds two words per key — the global offset of the first byte of
+ * the occurrence's line and of that line's newline (or the text length) — as krep_b200_scan_shard computes them on
+ * the device for -c plans (krep_b200_device_result_t.d_line_bounds, markers resolved).  A host that gathers keys from
+ * several newline-aligned shards gathers the bounds with them. */
+uint64_t krep_b200_replay_lines(int algo, const search_params_t *params, bool only_matching,
+                                const uint64_t *keys, uint64_t nkeys, const uint64_t *bounds,
+                                size_t text_len, match_result_t *result);
 
 /* AC key layout helpers */
 uint64_t krep_b200_ac_key_end(uint64_t key);

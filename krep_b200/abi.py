@@ -57,6 +57,7 @@ class DeviceResult(C.Structure):  # krep_b200_device_result_t
         ("d_keys", C.c_void_p),
         ("overflow", C.c_int),
         ("text_len", C.c_uint64),
+        ("d_line_bounds", C.c_void_p),
     ]
 
 

@@ -75,6 +75,7 @@ struct Plan
     uint8_t *d_pat_val = nullptr, *d_pat_mask = nullptr;
     bool border_free = true; // no proper prefix is also a suffix: occurrences cannot overlap
     bool built_only_matching = false; // value of the -o global the plan was compiled for
+    bool count_lines = false;         // -c: scan_shard also computes the line bounds of every occurrence on the device
     // AC
     std::vector<std::string> patterns;
     std::vector<uint32_t> pat_lens;
@@ -96,7 +97,14 @@ struct ScanOut
     uint64_t count = 0, stored = 0;
     const uint64_t *d_keys = nullptr;
     int overflow = 0;
+    const uint64_t *d_bounds = nullptr; // -c plans: 2 words per stored key (line start, line end), see k_line_bounds
 };
+
+// Line bounds of an occurrence, global offsets: [0] = first byte of its line, [1] = position of the line's '\n' (or
+// the text length).  The device writes these markers where the answer lies outside what one warp looked at:
+static constexpr uint64_t LB_SAME_AS_PREV = ~0ull;     // no newline between the previous occurrence and this one
+static constexpr uint64_t LB_SAME_AS_NEXT = ~0ull - 1; // no newline between this occurrence and the next one
+static constexpr uint64_t LB_OUTSIDE_SHARD = ~0ull - 2; // the line continues into a neighbouring shard
 
 // Launch one shard scan on `stream`; appends to the engine's key list (no reset) when append=true.
 int launch_scan(const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream);
@@ -123,9 +131,10 @@ struct Replay
 {
     const uint64_t *keys;
     size_t n;
-    const char *text; // host text (needed for -c line logic); may be null otherwise
+    const char *text; // host text (for -c line logic); may be null when `bounds` is given or -c is off
     size_t text_len;
     uint64_t base; // global offset subtracted from key offsets
+    const uint64_t *bounds = nullptr; // resolved line bounds, 2 per key (device-side -c): used when text is null
 };
 uint64_t replay_literal(int algo, const search_params_t *P, bool only_matching, uint32_t m,
                         const Replay &r, match_result_t *res);

@@ -111,6 +111,8 @@ void engine_shutdown()
     cudaFree(E.d_keys[0]);
     cudaFree(E.d_keys[1]);
     cudaFree(E.d_sort_tmp);
+    cudaFree(E.d_bounds);
+    cudaFreeHost(E.h_bounds);
     cudaFree(E.d_counter);
     cudaFree(E.d_text);
     cudaFreeHost(E.h_counter);
@@ -185,6 +187,7 @@ Plan *plan_build(const search_params_t *P, int algo, bool only_matching)
     Plan *pl = new Plan();
     pl->algo = algo;
     pl->case_sensitive = P->case_sensitive;
+    pl->count_lines = P->count_lines_mode;
     if (algo == KREP_B200_ALGO_AC)
     {
         pl->is_ac = true;
@@ -405,6 +408,97 @@ int key_end_bit(const Plan *plan, uint64_t max_offset)
     return b > 64 ? 64 : b;
 }
 
+// ---------------------------------------------------------------------------------------------
+// -c on the device: line bounds of every occurrence (find_line_start / find_line_end, krep.c:363-408), so that the
+// line-counting replay needs no host copy of the text.  One warp per (sorted) occurrence.  For literal plans the keys
+// are sorted by start, so the backward scan stops at the previous occurrence and the forward scan at the next one
+// (markers LB_SAME_AS_* are resolved by one pass on the host): the total work is O(text), however long the lines are.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_line_bounds(const uint8_t *__restrict__ text, uint64_t avail, uint64_t go,
+                                                     const uint64_t *__restrict__ keys, uint64_t n, int is_ac, int has_prev,
+                                                     int has_next, uint64_t *__restrict__ out)
+{
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    auto start_of = [&](uint64_t key) -> uint64_t {
+        if (!is_ac) return (key >> LIT_TAG_BITS) - go;
+        return (key >> AC_END_SHIFT) - (1024 - ((key >> AC_LEN_SHIFT) & 1023)) - go;
+    };
+    const uint64_t s = start_of(keys[i]);
+    const uint64_t lb = (!is_ac && i > 0) ? start_of(keys[i - 1]) : 0;       // backward scan covers [lb, s)
+    const uint64_t ub = (!is_ac && i + 1 < n) ? start_of(keys[i + 1]) : avail; // forward scan covers [s, ub)
+    // backward: last '\n' in [lb, s), 128 bytes per step (4 per lane)
+    uint64_t ls = (!is_ac && i > 0) ? LB_SAME_AS_PREV : (has_prev ? LB_OUTSIDE_SHARD : go);
+    for (uint64_t hi = s; hi > lb;)
+    {
+        const uint64_t w0 = hi >= lb + 128 ? hi - 128 : lb; // window [w0, hi)
+        int best = -1;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const uint64_t p = w0 + (uint64_t)lane * 4 + k;
+            if (p < hi && text[p] == '\n') best = lane * 4 + k;
+        }
+        best = __reduce_max_sync(0xffffffffu, best);
+        if (best >= 0)
+        {
+            ls = go + w0 + (uint64_t)best + 1;
+            break;
+        }
+        hi = w0;
+    }
+    // forward: first '\n' in [s, ub)
+    uint64_t le = (!is_ac && i + 1 < n) ? LB_SAME_AS_NEXT : (has_next ? LB_OUTSIDE_SHARD : go + avail);
+    for (uint64_t lo = s; lo < ub; lo += 128)
+    {
+        int best = 1 << 20;
+#pragma unroll
+        for (int k = 3; k >= 0; k--)
+        {
+            const uint64_t p = lo + (uint64_t)lane * 4 + k;
+            if (p < ub && text[p] == '\n') best = lane * 4 + k;
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (best < (1 << 20))
+        {
+            le = go + lo + (uint64_t)best;
+            break;
+        }
+    }
+    if (lane == 0)
+    {
+        out[2 * i] = ls;
+        out[2 * i + 1] = le;
+    }
+}
+
+static int line_bounds(const Plan *plan, const krep_b200_shard_t *sh, const uint64_t *d_sorted, uint64_t n, cudaStream_t stream,
+                       const uint64_t **d_bounds)
+{
+    Engine &E = g_engine;
+    *d_bounds = nullptr;
+    if (n == 0) return 0;
+    if (2 * n > E.bounds_cap)
+    {
+        CK(cudaStreamSynchronize(stream));
+        cudaFree(E.d_bounds);
+        E.d_bounds = nullptr;
+        E.bounds_cap = 0;
+        const uint64_t cap = 2 * n + n / 4 + 1024;
+        CK(cudaMalloc(&E.d_bounds, cap * sizeof(uint64_t)));
+        E.bounds_cap = cap;
+    }
+    const uint64_t threads = n * 32;
+    k_line_bounds<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>((const uint8_t *)sh->d_text, sh->avail_len, sh->global_offset,
+                                                                        d_sorted, n, plan->is_ac ? 1 : 0, sh->prev_byte >= 0,
+                                                                        sh->next_byte >= 0, E.d_bounds);
+    CK(cudaGetLastError());
+    count_launch();
+    *d_bounds = E.d_bounds;
+    return 0;
+}
+
 // Full single-shard scan: reset, launch (rerun with a larger list if it overflowed), sort.
 int scan_shard(const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream, ScanOut *out)
 {
@@ -436,7 +530,9 @@ int scan_shard(const Plan *plan, const krep_b200_shard_t *sh, int want_positions
         if (cnt <= E.key_cap)
         {
             out->stored = cnt;
-            return sort_keys(cnt, key_end_bit(plan, sh->global_offset + sh->avail_len), stream, &out->d_keys);
+            rc = sort_keys(cnt, key_end_bit(plan, sh->global_offset + sh->avail_len), stream, &out->d_keys);
+            if (rc == 0 && plan->count_lines) rc = line_bounds(plan, sh, out->d_keys, cnt, stream, &out->d_bounds);
+            return rc;
         }
         out->overflow = 1;
         if (ensure_keys(cnt + cnt / 8 + 1024) != 0) return -2;
@@ -546,6 +642,7 @@ int krep_b200_scan_shard(const krep_b200_plan_t *plan, const krep_b200_shard_t *
     out->d_keys = so.d_keys;
     out->overflow = so.overflow;
     out->text_len = shard->global_offset + shard->avail_len;
+    out->d_line_bounds = so.d_bounds;
     return rc;
 }
 

@@ -24,6 +24,10 @@ struct Engine
     uint64_t key_cap = 0;
     void *d_sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
+    uint64_t *d_bounds = nullptr; // -c: line bounds, 2 per key
+    uint64_t bounds_cap = 0;
+    uint64_t *h_bounds = nullptr; // pinned
+    uint64_t h_bounds_cap = 0;
     // host-text entry points: device copy of the caller's buffer + pinned staging ring + key readback
     uint8_t *d_text = nullptr;
     uint64_t text_cap = 0;

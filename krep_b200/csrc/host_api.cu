@@ -51,7 +51,7 @@ int resolve_algo(const search_params_t *P, int algo)
 // ---- plan cache ---------------------------------------------------------------------------------
 static bool plan_matches(const Plan *pl, const search_params_t *P, int algo, bool only_matching)
 {
-    if (pl->algo != algo || pl->case_sensitive != P->case_sensitive) return false;
+    if (pl->algo != algo || pl->case_sensitive != P->case_sensitive || pl->count_lines != P->count_lines_mode) return false;
     if (pl->is_ac)
     {
         if ((pl->whole_word != 0) != P->whole_word) return false;
@@ -585,6 +585,22 @@ uint64_t krep_b200_replay(int algo, const search_params_t *P, bool only_matching
     return replay_literal(algo, P, only_matching, m, r, result);
 }
 
+uint64_t krep_b200_replay_lines(int algo, const search_params_t *P, bool only_matching, const uint64_t *keys, uint64_t nkeys,
+                                const uint64_t *bounds, size_t text_len, match_result_t *result)
+{
+    if (!P) return 0;
+    if (P->count_lines_mode && !bounds && nkeys)
+    {
+        set_error(-3, "krep_b200_replay_lines: -c needs the line bounds");
+        return 0;
+    }
+    Replay r{keys, (size_t)nkeys, nullptr, text_len ? text_len : (SIZE_MAX >> 1), 0, bounds};
+    if (algo == KREP_B200_ALGO_AC) return replay_ac(P, r, result);
+    algo = resolve_algo(P, algo);
+    const uint32_t m = algo == KREP_B200_ALGO_MEMCHR ? 1u : (uint32_t)P->pattern_len;
+    return replay_literal(algo, P, only_matching, m, r, result);
+}
+
 // ---- shard result -> match_result_t under the emulated kernel's policy ----
 uint64_t krep_b200_collect(const krep_b200_plan_t *plan_, const search_params_t *P, const krep_b200_device_result_t *dev,
                            match_result_t *result)
@@ -593,9 +609,9 @@ uint64_t krep_b200_collect(const krep_b200_plan_t *plan_, const search_params_t 
     clear_error();
     const Plan *plan = reinterpret_cast<const Plan *>(plan_);
     if (!plan || !P || !dev) return 0;
-    if (P->count_lines_mode)
+    if (P->count_lines_mode && dev->stored && !dev->d_line_bounds)
     {
-        set_error(-3, "krep_b200_collect: -c line counting needs host text; use the search_func_t entry points");
+        set_error(-3, "krep_b200_collect: -c needs a plan created with count_lines_mode (line bounds are computed by the scan)");
         return 0;
     }
     ScanOut so;
@@ -606,6 +622,42 @@ uint64_t krep_b200_collect(const krep_b200_plan_t *plan_, const search_params_t 
     if (so.stored && fetch_keys(so, &keys) != 0) return 0;
     if (!so.stored) return limited_count(plan->algo, P, plan->is_ac || keeps_all(plan->algo, g_only_matching, P, plan) ? so.count : 0);
     Replay r{keys, (size_t)so.stored, nullptr, dev->text_len ? (size_t)dev->text_len : (SIZE_MAX >> 1), 0};
+    if (P->count_lines_mode)
+    {
+        // read the device-computed line bounds back and resolve the "same line as my neighbour" markers
+        Engine &E = engine();
+        const uint64_t nb = 2 * so.stored;
+        if (nb > E.h_bounds_cap)
+        {
+            cudaFreeHost(E.h_bounds);
+            E.h_bounds = nullptr;
+            E.h_bounds_cap = 0;
+            if (cudaMallocHost(&E.h_bounds, (nb + nb / 4 + 1024) * sizeof(uint64_t)) != cudaSuccess)
+            {
+                set_error(-2, "cannot allocate pinned memory for line bounds");
+                return 0;
+            }
+            E.h_bounds_cap = nb + nb / 4 + 1024;
+        }
+        if (cudaMemcpyAsync(E.h_bounds, dev->d_line_bounds, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, E.scan_stream) != cudaSuccess ||
+            cudaStreamSynchronize(E.scan_stream) != cudaSuccess)
+        {
+            set_error(-2, "reading line bounds back failed");
+            return 0;
+        }
+        uint64_t *b = E.h_bounds;
+        for (uint64_t i = 0; i < so.stored; i++)
+            if (b[2 * i] == LB_SAME_AS_PREV) b[2 * i] = i ? b[2 * (i - 1)] : LB_OUTSIDE_SHARD;
+        for (uint64_t i = so.stored; i-- > 0;)
+            if (b[2 * i + 1] == LB_SAME_AS_NEXT) b[2 * i + 1] = i + 1 < so.stored ? b[2 * (i + 1) + 1] : LB_OUTSIDE_SHARD;
+        for (uint64_t i = 0; i < nb; i++)
+            if (b[i] == LB_OUTSIDE_SHARD)
+            {
+                set_error(-3, "krep_b200_collect: a matching line continues into a neighbouring shard; -c needs newline-aligned shards");
+                return 0;
+            }
+        r.bounds = b;
+    }
     if (plan->is_ac) return replay_ac(P, r, result);
     return replay_literal(plan->algo, P, plan->built_only_matching, plan->m, r, result);
 }

@@ -55,6 +55,7 @@ struct Cursor
     const uint64_t *k;
     size_t n, i = 0;
     uint64_t base;
+    const uint64_t *bounds = nullptr; // device-computed line bounds (global offsets), 2 per key; used when no host text
     bool tail = false; // sub-buffer replay: an occurrence at position 0 has no byte before it (krep.h:314)
     size_t pos(size_t j) const { return (size_t)((k[j] >> LIT_TAG_BITS) - base); }
     bool full(size_t j) const { return (k[j] >> 2) & 1; }
@@ -62,6 +63,20 @@ struct Cursor
     void skip_below_base()
     {
         while (i < n && (k[i] >> LIT_TAG_BITS) < base) i++;
+    }
+    // find_line_start / find_line_end (krep.c:363-408) for the occurrence with key index j at position s, relative to
+    // this cursor's (sub-)buffer: from the host text when there is one, else from the device-computed bounds (a line
+    // start before the sub-buffer is clipped to it, exactly what memrchr over the sub-buffer returns).
+    size_t lstart(size_t j, const char *t, size_t len, size_t s) const
+    {
+        if (t || !bounds) return line_start(t, len, s);
+        return bounds[2 * j] > base ? (size_t)(bounds[2 * j] - base) : 0;
+    }
+    size_t lend(size_t j, const char *t, size_t len, size_t ls) const
+    {
+        if (t || !bounds) return line_end(t, len, ls);
+        const size_t e = (size_t)(bounds[2 * j + 1] - base);
+        return e < len ? e : len;
     }
     // index of the first full occurrence starting at or after `from`, or n
     size_t next_full(size_t from)
@@ -94,12 +109,12 @@ static uint64_t replay_bmh(const search_params_t *P, bool only_matching, size_t 
         bool bumped = false;
         if (P->count_lines_mode)
         {
-            const size_t ls = line_start(t, n, s);
+            const size_t ls = c.lstart(j, t, n, s);
             if (ls != last_line)
             {
                 cnt++; last_line = ls; bumped = true;
                 if (cnt >= P->max_count) break;
-                const size_t le = line_end(t, n, ls);
+                const size_t le = c.lend(j, t, n, ls);
                 const size_t nx = le < n ? le + 1 : n;
                 if (nx > s) { from = nx; continue; }
             }
@@ -130,12 +145,12 @@ static uint64_t replay_kmp(const search_params_t *P, size_t m, Cursor c, const c
         if (P->whole_word && !c.ww(j)) continue;
         if (P->count_lines_mode)
         {
-            const size_t ls = line_start(t, n, s);
+            const size_t ls = c.lstart(j, t, n, s);
             if (ls != last_line)
             {
                 if (P->max_count != SIZE_MAX && cnt >= P->max_count) break;
                 cnt++; last_line = ls;
-                const size_t le = line_end(t, n, ls);
+                const size_t le = c.lend(j, t, n, ls);
                 from = le < n ? le + 1 : n;
             }
         }
@@ -171,12 +186,12 @@ static uint64_t replay_memchr(const search_params_t *P, Cursor c, const char *t,
         if (P->whole_word && !c.ww(j)) { from = s + 1; continue; }
         if (P->count_lines_mode)
         {
-            const size_t ls = line_start(t, n, s);
+            const size_t ls = c.lstart(j, t, n, s);
             if (ls != last_line)
             {
                 if (P->max_count != SIZE_MAX && cnt >= P->max_count) break;
                 cnt++; last_line = ls;
-                const size_t le = line_end(t, n, ls);
+                const size_t le = c.lend(j, t, n, ls);
                 from = le < n ? le + 1 : n;
             }
             else from = s + 1;
@@ -237,12 +252,12 @@ static uint64_t replay_memchr_short(const search_params_t *P, bool only_matching
             bool bumped = false;
             if (P->count_lines_mode)
             {
-                const size_t ls = line_start(t, n, h);
+                const size_t ls = c.lstart(j, t, n, h);
                 if (ls != last_line)
                 {
                     cnt++; last_line = ls; bumped = true;
                     if (cnt >= P->max_count) break;
-                    const size_t le = line_end(t, n, ls);
+                    const size_t le = c.lend(j, t, n, ls);
                     const size_t nx = le < n ? le + 1 : n;
                     if (nx > cur) { cur = nx; continue; }
                 }
@@ -291,12 +306,12 @@ static uint64_t replay_sse42(const search_params_t *P, bool only_matching, size_
             bool bumped = false;
             if (P->count_lines_mode)
             {
-                const size_t ls = line_start(t, n, s);
+                const size_t ls = c.lstart(j, t, n, s);
                 if (ls != last_line)
                 {
                     if (cnt >= P->max_count) break;
                     cnt++; last_line = ls; bumped = true;
-                    const size_t le = line_end(t, n, ls);
+                    const size_t le = c.lend(j, t, n, ls);
                     if (le < n) { cur = wcur + ((le + 1) - s); continue; }
                 }
             }
@@ -349,12 +364,12 @@ static uint64_t replay_window(const search_params_t *P, bool only_matching, size
             bool bumped = false;
             if (P->count_lines_mode)
             {
-                const size_t ls = line_start(t, n, s);
+                const size_t ls = c.lstart(j, t, n, s);
                 if (ls != last_line)
                 {
                     cnt++; last_line = ls; bumped = true;
                     if (cnt >= maxc) return cnt;
-                    const size_t le = line_end(t, n, ls);
+                    const size_t le = c.lend(j, t, n, ls);
                     const size_t nx = le < n ? le + 1 : n;
                     if (nx > cur)
                     {
@@ -414,7 +429,7 @@ static uint64_t replay_window(const search_params_t *P, bool only_matching, size
 uint64_t replay_literal(int algo, const search_params_t *P, bool only_matching, uint32_t m, const Replay &r,
                         match_result_t *res)
 {
-    Cursor c{r.keys, r.n, 0, r.base};
+    Cursor c{r.keys, r.n, 0, r.base, r.text ? nullptr : r.bounds};
     switch (algo)
     {
     case KREP_B200_ALGO_AVX2: return replay_window(P, only_matching, m, 32, c, r.text, r.text_len, res);   // resolved: 17..32 B
@@ -443,7 +458,8 @@ uint64_t replay_ac(const search_params_t *P, const Replay &r, match_result_t *re
         const size_t s = e - len;
         if (P->count_lines_mode)
         {
-            const size_t ls = line_start(r.text, r.text_len, s);
+            const size_t ls = (r.text || !r.bounds) ? line_start(r.text, r.text_len, s)
+                                                    : (r.bounds[2 * j] > r.base ? (size_t)(r.bounds[2 * j] - r.base) : 0);
             if (ls != last_line)
             {
                 found++; last_line = ls;

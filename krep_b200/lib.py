@@ -76,6 +76,9 @@ def load():
     L.krep_b200_replay.argtypes = [C.c_int, C.POINTER(SearchParams), C.c_bool, C.POINTER(C.c_uint64), C.c_uint64,
                                    C.c_void_p, C.c_size_t, C.POINTER(MatchResult)]
     L.krep_b200_replay.restype = C.c_uint64
+    L.krep_b200_replay_lines.argtypes = [C.c_int, C.POINTER(SearchParams), C.c_bool, C.POINTER(C.c_uint64), C.c_uint64,
+                                         C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(MatchResult)]
+    L.krep_b200_replay_lines.restype = C.c_uint64
     L.krep_b200_export_keys.argtypes = [C.POINTER(DeviceResult), C.c_void_p, C.c_uint64, C.c_void_p]
     L.krep_b200_export_keys.restype = C.c_int
     L.krep_b200_last_kernel_ms.restype = C.c_float

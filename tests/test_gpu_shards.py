@@ -115,3 +115,52 @@ def test_properties_at_1gib():
         assert pa + pb == pos and ca + cb == cnt
     finally:
         L.krep_b200_plan_destroy(plan)
+
+
+def _texts_for_line_counting():
+    import random
+    rng = random.Random(31)
+    words = [b"needle", b"the", b"quick", b"ab", b"abab", b"NEEDLE", b"x", b"haystack", b"aaa"]
+    out = []
+    for n, nl in [(200, 0.3), (5_000, 0.1), (300_000, 0.02), (300_000, 0.0005), (50_000, 0.0)]:
+        t = bytearray()
+        while len(t) < n:
+            t += rng.choice(words) + (b"\n" if rng.random() < nl else rng.choice([b" ", b"", b"_", b", "]))
+        out.append(bytes(t[:n]))
+    out.append(b"\n" * 40 + b"needle\n\nneedle needle\n" + b"x" * 300 + b"needle")
+    return out
+
+
+@pytest.mark.parametrize("func,algo,pats,opts", [
+    ("boyer_moore", ALGO_BMH, [b"needle"], dict()),
+    ("boyer_moore", ALGO_BMH, [b"ab"], dict(whole_word=True)),
+    ("boyer_moore", ALGO_BMH, [b"aaa"], dict(max_count=7)),
+    ("sse42", ALGO_SSE42, [b"abab"], dict()),
+    ("sse42", ALGO_SSE42, [b"the quick"], dict()),
+    ("kmp", 1, [b"abab"], dict()),
+    ("memchr", 2, [b"x"], dict()),
+    ("memchr_short", 3, [b"ab"], dict(case_sensitive=False)),
+    ("avx2", 5, [b"needle the quick ab"], dict()),
+    ("aho_corasick", ALGO_AC, [b"needle", b"quick", b"ab", b"haystack"], dict()),
+    ("aho_corasick", ALGO_AC, [b"needle", b"haystack", b"quick the"], dict(case_sensitive=False, max_count=5)),
+])
+def test_count_lines_on_the_device(func, algo, pats, opts):
+    """-c for an HBM-resident shard: the scan computes every occurrence's line bounds on the GPU (k_line_bounds) and the
+    replay counts lines from them — no host copy of the text is involved.  Must equal the reference's -c result."""
+    L = lib.load()
+    for text in _texts_for_line_counting():
+        p = Params(pats, count=True, **opts)
+        if func == "aho_corasick":
+            p.struct.ac_trie = 1
+        plan = L.krep_b200_plan_create(p.ref(), algo)
+        lib.check(L)
+        try:
+            dev = gu.to_device(text)
+            out = gu.scan(plan, dev, len(text))
+            got = gu.collect(plan, p, out)
+            p.struct.ac_trie = None
+            want = checker().run(func, Params(pats, count=True, **opts), text)
+            assert got == want, (func, pats, opts, len(text), got, want)
+        finally:
+            p.struct.ac_trie = None
+            L.krep_b200_plan_destroy(plan)

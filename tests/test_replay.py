@@ -125,3 +125,48 @@ def test_replay_matches_oracle(func):
             assert got == want, (chk.kind, func, pats, text, opts, with_res, got, want)
         n_checked += 1
     assert n_checked > 500
+
+
+def _bounds_for(func, keys, text):
+    """Line bounds as k_line_bounds delivers them (after marker resolution): per key the first byte of the line that
+    holds the occurrence's start and the position of that line's newline (or the text length)."""
+    out = []
+    for k in keys:
+        if func == "aho_corasick":
+            e = k >> 24
+            s = e - (1024 - ((k >> 14) & 1023))
+        else:
+            s = k >> 3
+        ls = text.rfind(b"\n", 0, s) + 1
+        le = text.find(b"\n", s)
+        out += [ls, len(text) if le < 0 else le]
+    return out
+
+
+@pytest.mark.parametrize("func", list(ALGO))
+def test_count_lines_replay_from_line_bounds_only(func):
+    """-c without any host text: the replay reads line starts / ends from the per-occurrence bounds."""
+    rng = random.Random(991 + ALGO[func])
+    L = lib.load()
+    chk = ou.port()
+    n_checked = 0
+    for _ in range(4000):
+        pats, text, opts, _ = random_case(rng, func)
+        opts = dict(opts, count=True, only_matching=False)
+        if func == "sse42" and (len(pats[0]) > 16 or not opts["case_sensitive"]):
+            continue
+        p = Params(pats, **opts)
+        if early_out(func, p, text):
+            continue
+        keys = device_like_keys(func, pats, text, opts["case_sensitive"], opts["whole_word"], False)
+        bounds = _bounds_for(func, keys, text)
+        arr = (C.c_uint64 * max(len(keys), 1))(*keys)
+        barr = (C.c_uint64 * max(len(bounds), 1))(*bounds)
+        if func == "aho_corasick":
+            p.struct.ac_trie = 1
+        cnt = L.krep_b200_replay_lines(ALGO[func], p.ref(), False, arr, len(keys), barr, len(text), None)
+        p.struct.ac_trie = None
+        want = chk.run(func, Params(pats, **opts), text, with_result=False)
+        assert int(cnt) == want[0], (func, pats, text, opts, int(cnt), want[0])
+        n_checked += 1
+    assert n_checked > 300
