@@ -604,6 +604,7 @@ __device__ __forceinline__ unsigned tri4_verify_batch(const AcDev &A, uint32_t s
         const uint32_t b = __ballot_sync(0xffffffffu, km != 0);
         if (b)
         {
+            __syncwarp(); // the slots written below may be the ones other lanes have just read their entries from
             if (km)
             {
                 const uint32_t e = q_base + (qn + __popc(b & lt_mask)) * TRI4_ENTRY;
