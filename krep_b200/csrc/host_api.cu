@@ -171,9 +171,21 @@ static cudaEvent_t pool_event(size_t idx)
     return E.ev_pool[idx];
 }
 
+static int copy_threads()
+{
+    static int nt = 0;
+    if (!nt)
+    {
+        const char *v = getenv("KREP_B200_COPY_THREADS");
+        nt = v ? atoi(v) : 8; // host threads (8 already saturate the PCIe link: 53 GB/s measured; 32+ oversubscribe and halve it) that move the caller's (pageable) text into the pinned staging ring
+        nt = std::max(1, std::min(nt, std::max(1, omp_get_num_procs())));
+    }
+    return nt;
+}
+
 static void parallel_copy(uint8_t *dst, const uint8_t *src, size_t n)
 {
-    const int nt = std::min(8, std::max(1, omp_get_max_threads()));
+    const int nt = copy_threads();
     if (n < (8u << 20) || nt == 1)
     {
         memcpy(dst, src, n);

@@ -1,0 +1,26 @@
+#!/bin/bash
+# What a krep user sees: the stock CLI vs the same CLI relinked against libkrep_b200.so, whole-process wall time,
+# on a corpus file in /dev/shm (page cache).  Usage: bash scripts/gpu_cli_timing.sh [GiB]
+G=${1:-8}; O=gpurun_out; mkdir -p $O
+python - <<PY
+import ctypes as C, sys, torch
+sys.path.insert(0, ".")
+import bench
+from krep_b200 import lib
+L = lib.load(); assert L.krep_b200_init(0) == 0
+n = int($G * (1 << 30))
+spec = lib.make_spec(bench.SEED, bench.PLANT_SEED, 1 << 20, b"qzXv9Kpw", 0)
+t = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+L.krep_b200_corpus_generate(C.byref(spec), t.data_ptr(), 0, n, None)
+t[:n].cpu().numpy().tofile("/dev/shm/krep_cli_corpus.txt")
+open("/dev/shm/krep_cli_pats.txt", "wb").write(b"\n".join(bench.multi_patterns(1000, b"kqzvxjwpy")) + b"\n")
+PY
+F=/dev/shm/krep_cli_corpus.txt; P=/dev/shm/krep_cli_pats.txt
+run() { local s=$(date +%s.%N); "$@" > /tmp/cli_out.txt 2>/tmp/cli_err.txt; local rc=$?; local e=$(date +%s.%N); echo "$(echo "$e - $s" | bc -l 2>/dev/null || python -c "print($e-$s)") s rc=$rc out=$(tail -c 80 /tmp/cli_out.txt | tr '\n' ' ')"; }
+for args in "-c qzXv9Kpw" "-c -o qzXv9Kpw" "-c -i QzXv" "-c -w needleneedle0016" "-c -o -f $P"; do
+  for bin in oracle/_ref/krep build/krep_gpu/krep; do
+    run $bin $args $F > /dev/null   # warm
+    echo "$bin $args : $(run $bin $args $F)"
+  done
+done | tee $O/cli_timing.txt
+rm -f $F $P
