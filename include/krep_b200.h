@@ -115,6 +115,8 @@ uint64_t krep_b200_simd_sse42_search(const search_params_t *, const char *, size
 uint64_t krep_b200_simd_avx2_search(const search_params_t *, const char *, size_t, match_result_t *);    /* krep.c:4877 */
 uint64_t krep_b200_simd_avx512_search(const search_params_t *, const char *, size_t, match_result_t *);  /* krep.c:5108 */
 uint64_t krep_b200_aho_corasick_search(const search_params_t *, const char *, size_t, match_result_t *); /* aho_corasick.c:299 */
+/* the ARM build's kernel; never chosen by krep_b200_select_search_algorithm (which stands in for the x86 AVX2 build) */
+uint64_t krep_b200_neon_search(const search_params_t *, const char *, size_t, match_result_t *);          /* krep.c:4506 */
 
 /* krep.c:1771 — same decision order (regex excluded: returns NULL for
  * use_regex, the caller keeps its own regex_search), same globals. The
@@ -156,7 +158,8 @@ enum
    KREP_B200_ALGO_SSE42 = 4,        /* simd_sse42_search   krep.c:4702 */
    KREP_B200_ALGO_AVX2 = 5,         /* simd_avx2_search    krep.c:4877 */
    KREP_B200_ALGO_AVX512 = 6,       /* simd_avx512_search  krep.c:5108 */
-   KREP_B200_ALGO_AC = 7            /* aho_corasick_search aho_corasick.c:299 */
+   KREP_B200_ALGO_AC = 7,           /* aho_corasick_search aho_corasick.c:299 */
+   KREP_B200_ALGO_NEON = 8          /* neon_search         krep.c:4506 */
 };
 
 typedef struct krep_b200_plan krep_b200_plan_t; /* compiled pattern set, device-resident */

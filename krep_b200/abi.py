@@ -75,7 +75,7 @@ class CorpusSpec(C.Structure):  # krep_b200_corpus_spec_t
 CORPUS_RANDOM_CASE = 1
 CORPUS_EMBED_HALF = 2
 
-ALGO_BMH, ALGO_KMP, ALGO_MEMCHR, ALGO_MEMCHR_SHORT, ALGO_SSE42, ALGO_AVX2, ALGO_AVX512, ALGO_AC = range(8)
+ALGO_BMH, ALGO_KMP, ALGO_MEMCHR, ALGO_MEMCHR_SHORT, ALGO_SSE42, ALGO_AVX2, ALGO_AVX512, ALGO_AC, ALGO_NEON = range(9)
 
 
 class Params:

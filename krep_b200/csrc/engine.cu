@@ -238,7 +238,7 @@ Plan *plan_build(const search_params_t *P, int algo, bool only_matching)
         // rejected occurrences in the list — but only if occurrences can overlap at all.  Prefix plans always tag.
         bool tag = pl->emit_len != pl->m;
         // the window kernels' tail sub-search re-evaluates -w against its sub-buffer (krep.c:5068): needs both halves
-        if (algo == KREP_B200_ALGO_AVX2 || algo == KREP_B200_ALGO_AVX512) tag = true;
+        if (algo == KREP_B200_ALGO_AVX2 || algo == KREP_B200_ALGO_AVX512 || algo == KREP_B200_ALGO_NEON) tag = true;
         if (!tag && !pl->border_free)
             tag = algo == KREP_B200_ALGO_KMP || (algo == KREP_B200_ALGO_SSE42 && !only_matching);
         pl->whole_word = tag ? 2 : 1;

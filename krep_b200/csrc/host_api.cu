@@ -45,6 +45,7 @@ int resolve_algo(const search_params_t *P, int algo)
     {
         if (m == 0 || m > 16 || !P->case_sensitive) return KREP_B200_ALGO_BMH;
     }
+    if (algo == KREP_B200_ALGO_NEON && (m == 0 || !P->case_sensitive)) return KREP_B200_ALGO_BMH; // krep.c:4511
     return algo;
 }
 
@@ -325,7 +326,7 @@ static bool keeps_all(int algo, bool only_matching, const search_params_t *P, co
     if (pl->is_ac) return true;
     if (pl->emit_len != pl->m) return false;
     // window kernels: tail sub-search, AVX-512's skipped windows and the -m re-basing all need the list
-    if (algo == KREP_B200_ALGO_AVX2 || algo == KREP_B200_ALGO_AVX512) return false;
+    if (algo == KREP_B200_ALGO_AVX2 || algo == KREP_B200_ALGO_AVX512 || algo == KREP_B200_ALGO_NEON) return false;
     if (pl->border_free) return true; // occurrences cannot overlap: every overlap policy keeps all
     switch (algo)
     {
@@ -465,6 +466,10 @@ uint64_t krep_b200_aho_corasick_search(const search_params_t *p, const char *t, 
 {
     return run_search(KREP_B200_ALGO_AC, p, t, n, r);
 }
+uint64_t krep_b200_neon_search(const search_params_t *p, const char *t, size_t n, match_result_t *r)
+{
+    return run_search(KREP_B200_ALGO_NEON, p, t, n, r);
+}
 
 // krep.c:1873-1914
 static bool is_repetitive_pattern(const char *pattern, size_t len)
@@ -522,6 +527,7 @@ const char *krep_b200_get_algorithm_name(search_func_t f)
     if (f == krep_b200_simd_sse42_search) return "SSE4.2";
     if (f == krep_b200_simd_avx2_search) return "AVX2";
     if (f == krep_b200_simd_avx512_search) return "AVX-512";
+    if (f == krep_b200_neon_search) return "NEON";
     return "Unknown";
 }
 

@@ -334,10 +334,14 @@ static uint64_t replay_sse42(const search_params_t *P, bool only_matching, size_
 // ascending order (overlaps included, whatever -o says); -c re-aims the cursor at the next line; the < W tail is a
 // boyer_moore_search on the SUB-buffer (its own -w / -c context, -o advance, re-based -m) whose positions are then
 // re-based by index arithmetic on the result vector; AVX-512 skips a window when < (m-1)+64 bytes remain (krep.c:5171).
+// neon_search (W = 16, krep.c:4506-4694, any needle length) walks the same way with three differences: the -m limit is
+// also tested before counting, the -c jump needs the line to end in a newline, and the tail's positions are re-based
+// over the last tail_count entries of the result vector.
 static uint64_t replay_window(const search_params_t *P, bool only_matching, size_t m, size_t W, Cursor c, const char *t,
                               size_t n, match_result_t *res)
 {
     if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
+    const bool neon = W == 16;
     const size_t maxc = P->max_count;
     uint64_t cnt = 0;
     size_t last_line = SIZE_MAX, cur = 0;
@@ -367,11 +371,12 @@ static uint64_t replay_window(const search_params_t *P, bool only_matching, size
                 const size_t ls = c.lstart(j, t, n, s);
                 if (ls != last_line)
                 {
+                    if (neon && cnt >= maxc) return cnt; // krep.c:4571
                     cnt++; last_line = ls; bumped = true;
-                    if (cnt >= maxc) return cnt;
+                    if (!neon && cnt >= maxc) return cnt;
                     const size_t le = c.lend(j, t, n, ls);
                     const size_t nx = le < n ? le + 1 : n;
-                    if (nx > cur)
+                    if (nx > cur && !(neon && le >= n)) // krep.c:4578: NEON only jumps when the line has a newline
                     {
                         cur = nx; // advance is clipped to the remaining length, i.e. cur <= n (nx <= n already)
                         line_skipped = true;
@@ -381,6 +386,7 @@ static uint64_t replay_window(const search_params_t *P, bool only_matching, size
             }
             else
             {
+                if (neon && cnt >= maxc) return cnt; // krep.c:4601
                 cnt++; bumped = true;
                 if (P->track_positions && res && cnt <= maxc) result_push(res, s, s + m);
             }
@@ -401,7 +407,16 @@ static uint64_t replay_window(const search_params_t *P, bool only_matching, size
         const uint64_t tcnt = replay_bmh(&tail, only_matching, m, tc, t ? t + cur : nullptr, rem, res);
         if (res && P->track_positions && tcnt > 0)
         {
-            if (W == 32)
+            if (neon)
+            {
+                if (res->count >= tcnt) // krep.c:4673-4680
+                    for (uint64_t k = 0; k < tcnt; k++)
+                    {
+                        res->positions[res->count - tcnt + k].start_offset += cur;
+                        res->positions[res->count - tcnt + k].end_offset += cur;
+                    }
+            }
+            else if (W == 32)
             {
                 const uint64_t b0 = cnt > res->count ? res->count : cnt; // krep.c:5077-5079
                 for (uint64_t k = b0; k < res->count; k++)
@@ -434,6 +449,7 @@ uint64_t replay_literal(int algo, const search_params_t *P, bool only_matching, 
     {
     case KREP_B200_ALGO_AVX2: return replay_window(P, only_matching, m, 32, c, r.text, r.text_len, res);   // resolved: 17..32 B
     case KREP_B200_ALGO_AVX512: return replay_window(P, only_matching, m, 64, c, r.text, r.text_len, res); // resolved: 33..64 B
+    case KREP_B200_ALGO_NEON: return replay_window(P, only_matching, m, 16, c, r.text, r.text_len, res);
     case KREP_B200_ALGO_KMP: return replay_kmp(P, m, c, r.text, r.text_len, res);
     case KREP_B200_ALGO_MEMCHR: return replay_memchr(P, c, r.text, r.text_len, res);
     case KREP_B200_ALGO_MEMCHR_SHORT: return replay_memchr_short(P, only_matching, m, c, r.text, r.text_len, res);

@@ -21,6 +21,7 @@ SEARCH_ENTRIES = {
     "avx2": "krep_b200_simd_avx2_search",
     "avx512": "krep_b200_simd_avx512_search",
     "aho_corasick": "krep_b200_aho_corasick_search",
+    "neon": "krep_b200_neon_search",
 }
 
 _lib = None

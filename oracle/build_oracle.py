@@ -5,6 +5,8 @@
                              through oracle/ref_wrap.c (adds accessors for krep.c's static flags)
   _ref/krep               <- the stock reference CLI, same sources, with its own main()
   _ref/libkrep_ref512.so  <- the same library as its AVX-512 build (adds simd_avx512_search)
+  _ref/libkrep_refneon.so <- the same library as its NEON build (adds neon_search), compiled on x86 against
+                             oracle/neon_shim/arm_neon.h (scalar stand-ins for the five intrinsics it uses)
 
 The reference's own Makefile is NOT run; its flag set (Makefile:9-41) is restated here:
 -O3 -std=c11 -pthread -D_GNU_SOURCE -D_DEFAULT_SOURCE -funroll-loops, SIMD flags fixed to
@@ -86,7 +88,25 @@ def build_ref512(force=False):
     return lib
 
 
+def build_refneon(force=False):
+    """The reference's ARM path (neon_search, krep.c:4506) compiled here: no x86 SIMD flags, -D__ARM_NEON, and
+    oracle/neon_shim/arm_neon.h standing in for the five intrinsics it uses.  Pins oracle_neon_search."""
+    lib = os.path.join(OUT_REF, "libkrep_refneon.so")
+    if not ref_available():
+        return lib if os.path.exists(lib) else None
+    os.makedirs(OUT_REF, exist_ok=True)
+    srcs = [os.path.join(REF_DIR, f) for f in ("krep.c", "aho_corasick.c", "krep.h", "aho_corasick.h")]
+    wrap = os.path.join(HERE, "ref_wrap.c")
+    shim = os.path.join(HERE, "neon_shim")
+    if force or _stale(lib, srcs + [wrap, os.path.join(shim, "arm_neon.h")]):
+        flags = [f for f in CFLAGS if f not in ("-msse4.2", "-mavx2")]
+        _run(["gcc", *flags, "-mno-sse4.2", "-mno-avx", "-D__ARM_NEON", "-DTESTING", "-fPIC", "-shared", "-I", shim, "-I", REF_DIR,
+              "-o", lib, wrap, os.path.join(REF_DIR, "aho_corasick.c")])
+    return lib
+
+
 if __name__ == "__main__":
     print(build_port(force="--force" in sys.argv))
     print(build_ref(force="--force" in sys.argv))
     print(build_ref512(force="--force" in sys.argv))
+    print(build_refneon(force="--force" in sys.argv))

@@ -515,6 +515,79 @@ uint64_t oracle_avx512_search(const search_params_t *P, const char *text, size_t
 }
 
 /* ==========================================================================
+ * neon_search — krep.c:4506-4694 (the ARM build's kernel for every
+ * case-sensitive needle; pinned against the reference's own source compiled
+ * here with scalar stand-ins for its five NEON intrinsics, build_oracle.py).
+ * 16-byte windows from a cursor; every start in the window whose first byte
+ * matches is memcmp-verified in ascending order (overlaps kept, any needle
+ * length).  Differs from the AVX2 walk in three observable ways: the -m limit
+ * is tested BEFORE counting as well (krep.c:4571, 4601), the -c jump to the next
+ * line only happens when the line has a newline (krep.c:4578), and the tail's
+ * positions are re-based over the last tail_count entries (krep.c:4673-4680).
+ * ========================================================================== */
+uint64_t oracle_neon_search(const search_params_t *P, const char *text, size_t n, match_result_t *res)
+{
+    const size_t m = P->pattern_len, maxc = P->max_count;
+    if (m == 0 || !P->case_sensitive || n < m) return oracle_boyer_moore_search(P, text, n, res);
+    if (maxc == 0 && (P->count_lines_mode || P->track_positions)) return 0;
+    const unsigned char *t = (const unsigned char *)text, *p = (const unsigned char *)P->pattern;
+    uint64_t cnt = 0;
+    size_t last_line = SIZE_MAX, cur = 0, rem = n;
+    while (rem >= 16)
+    {
+        bool jumped = false;
+        for (size_t i = 0; i < 16; i++)
+        {
+            if (t[cur + i] != p[0] || rem - i < m || !occurs(t + cur + i, p, m, true)) continue;
+            const size_t s = cur + i;
+            if (P->whole_word && !whole_word(text, n, s, s + m)) continue;
+            bool bumped = false;
+            if (P->count_lines_mode)
+            {
+                const size_t ls = line_start(text, n, s);
+                if (ls != last_line)
+                {
+                    if (cnt >= maxc) return cnt;
+                    cnt++; last_line = ls; bumped = true;
+                    const size_t le = line_end(text, n, ls);
+                    if (le < n && le + 1 > cur)
+                    {
+                        size_t adv = le + 1 - cur;
+                        if (adv > rem) adv = rem;
+                        cur += adv; rem -= adv;
+                        jumped = true;
+                        break;
+                    }
+                }
+            }
+            else
+            {
+                if (cnt >= maxc) return cnt;
+                cnt++; bumped = true;
+                if (P->track_positions && res && cnt <= maxc) push(res, s, s + m);
+            }
+            if (bumped && cnt >= maxc) return cnt;
+        }
+        if (jumped) continue;
+        cur += 16; rem -= 16;
+    }
+    if (rem >= m)
+    {
+        search_params_t tail = *P;
+        if (maxc != SIZE_MAX) tail.max_count = cnt >= maxc ? 0 : maxc - cnt;
+        const uint64_t tc = oracle_boyer_moore_search(&tail, text + cur, rem, res);
+        if (res && P->track_positions && tc > 0 && res->count >= tc)
+            for (uint64_t k = 0; k < tc; k++)
+            {
+                res->positions[res->count - tc + k].start_offset += cur;
+                res->positions[res->count - tc + k].end_offset += cur;
+            }
+        cnt += tc;
+    }
+    return cnt;
+}
+
+/* ==========================================================================
  * ac_trie_build / aho_corasick_search — aho_corasick.c:111-271, 299-466.
  * Restated with array-indexed nodes.  Emission order: ascending end offset;
  * at one end offset the deepest node first, then along the failure chain;

@@ -23,6 +23,8 @@ FUNCS = {
 }
 # only present in an AVX-512 build of the reference (oracle/_ref/libkrep_ref512.so)
 FUNCS_512 = {"avx512": ("oracle_avx512_search", "simd_avx512_search")}
+# only present in the reference's ARM build (oracle/_ref/libkrep_refneon.so: compiled here against a scalar arm_neon.h)
+FUNCS_NEON = {"neon": ("oracle_neon_search", "neon_search")}
 
 
 class _Checker:
@@ -85,7 +87,7 @@ _cache = {}
 
 def port():
     if "port" not in _cache:
-        _cache["port"] = _Checker(C.CDLL(build_oracle.build_port()), "port", {**FUNCS, **FUNCS_512})
+        _cache["port"] = _Checker(C.CDLL(build_oracle.build_port()), "port", {**FUNCS, **FUNCS_512, **FUNCS_NEON})
     return _cache["port"]
 
 
@@ -111,6 +113,15 @@ def reference512():
                 ok = False
         _cache["ref512"] = _Checker(C.CDLL(lib), "reference", {**FUNCS, **FUNCS_512}) if ok else None
     return _cache["ref512"]
+
+
+def reference_neon():
+    """The reference's NEON kernel compiled on x86 (see build_oracle.build_refneon), or None."""
+    if "refneon" not in _cache:
+        lib = build_oracle.build_refneon()
+        base = {k: v for k, v in FUNCS.items() if k not in ("sse42", "avx2")}  # no x86 SIMD kernels in that build
+        _cache["refneon"] = _Checker(C.CDLL(lib), "reference", {**base, **FUNCS_NEON}) if lib else None
+    return _cache["refneon"]
 
 
 def ref_cli():

@@ -37,10 +37,10 @@ def test_committed_reference_fixtures_through_c_abi():
         assert cnt == c["count_out"] and [list(x) for x in pos] == c["pos_out"], c
 
 
-@pytest.mark.parametrize("func", list(ou.FUNCS) + ["avx512"])
+@pytest.mark.parametrize("func", list(ou.FUNCS) + ["avx512", "neon"])
 def test_random_differential_vs_oracle(func):
     rng = random.Random(4242 + len(func))
-    chk = (ou.reference512() or ou.port()) if func == "avx512" else checker()
+    chk = {"avx512": ou.reference512() or ou.port(), "neon": ou.reference_neon() or ou.port()}.get(func) or checker()
     for _ in range(700):
         pats, text, opts, with_res = random_case(rng, func)
         got = lib.search(func, Params(pats, **opts), text, with_result=with_res)

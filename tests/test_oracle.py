@@ -109,9 +109,9 @@ def random_case(rng, func):
             pats.append(pats[0])  # duplicate pattern -> duplicate emissions (aho_corasick.c:361)
     else:
         lo, hi = {"memchr": (1, 1), "memchr_short": (2, 3), "sse42": (1, 18), "avx2": (14, 36),
-                  "avx512": (28, 70)}.get(func, (1, 20))
+                  "avx512": (28, 70), "neon": (1, 24)}.get(func, (1, 20))
         m = rng.randint(lo, hi)
-        if (func in ("avx2", "avx512") and rng.random() < 0.5) or rng.random() < 0.25:
+        if (func in ("avx2", "avx512", "neon") and rng.random() < 0.5) or rng.random() < 0.25:
             # periodic needle + periodic text: many overlapping occurrences, window / tail edges everywhere
             unit = bytes(rng.choice(alpha) for _ in range(rng.randint(1, 3)))
             m = min(m, rng.choice([m, m, 2, 3, 4, 6]))
@@ -129,7 +129,7 @@ def random_case(rng, func):
             pat = pat.swapcase()
         pats = [pat]
     opts = dict(
-        case_sensitive=rng.random() < (0.9 if func in ("avx2", "avx512") else 0.5),
+        case_sensitive=rng.random() < (0.9 if func in ("avx2", "avx512", "neon") else 0.5),
         count=rng.random() < 0.35,
         only_matching=rng.random() < 0.4,
         whole_word=rng.random() < 0.35,
@@ -163,4 +163,18 @@ def test_port_vs_avx512_build_of_the_reference():
         pats, text, opts, with_res = random_case(rng, "avx512")
         a = ou.port().run("avx512", Params(pats, **opts), text, with_result=with_res)
         b = ref.run("avx512", Params(pats, **opts), text, with_result=with_res)
+        assert a == b, (pats, text, opts, with_res, a, b)
+
+
+def test_port_vs_neon_build_of_the_reference():
+    """neon_search only exists in the reference's ARM build; its source is compiled here against a scalar arm_neon.h
+    (five intrinsics) and pins oracle_neon_search."""
+    ref = ou.reference_neon()
+    if ref is None:
+        pytest.skip("NEON build of the reference not available")
+    rng = random.Random(9)
+    for it in range(4000):
+        pats, text, opts, with_res = random_case(rng, "neon")
+        a = ou.port().run("neon", Params(pats, **opts), text, with_result=with_res)
+        b = ref.run("neon", Params(pats, **opts), text, with_result=with_res)
         assert a == b, (pats, text, opts, with_res, a, b)

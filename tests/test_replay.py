@@ -9,12 +9,12 @@ import pytest
 
 import oracle_util as ou
 from krep_b200 import lib
-from krep_b200.abi import (ALGO_AC, ALGO_AVX2, ALGO_AVX512, ALGO_BMH, ALGO_KMP, ALGO_MEMCHR, ALGO_MEMCHR_SHORT, ALGO_SSE42,
-                           MatchResult, Params, SIZE_MAX)
+from krep_b200.abi import (ALGO_AC, ALGO_AVX2, ALGO_AVX512, ALGO_BMH, ALGO_KMP, ALGO_MEMCHR, ALGO_MEMCHR_SHORT, ALGO_NEON,
+                           ALGO_SSE42, MatchResult, Params, SIZE_MAX)
 from test_oracle import random_case
 
 ALGO = {"boyer_moore": ALGO_BMH, "kmp": ALGO_KMP, "memchr": ALGO_MEMCHR, "memchr_short": ALGO_MEMCHR_SHORT,
-        "sse42": ALGO_SSE42, "aho_corasick": ALGO_AC, "avx2": ALGO_AVX2, "avx512": ALGO_AVX512}
+        "sse42": ALGO_SSE42, "aho_corasick": ALGO_AC, "avx2": ALGO_AVX2, "avx512": ALGO_AVX512, "neon": ALGO_NEON}
 
 
 def lc(b):
@@ -108,6 +108,8 @@ def test_replay_matches_oracle(func):
     rng = random.Random(77 + ALGO[func])
     if func == "avx512":
         checkers = [ou.port()] + ([ou.reference512()] if ou.reference512() else [])
+    elif func == "neon":
+        checkers = [ou.port()] + ([ou.reference_neon()] if ou.reference_neon() else [])
     else:
         checkers = [ou.port()] + ([ou.reference()] if ou.reference() else [])
     n_checked = 0
