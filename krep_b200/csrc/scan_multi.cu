@@ -9,11 +9,15 @@
 //   * SAMPLED WINDOW FILTER.  With Lmin the shortest pattern, pick a window width w and a sampling
 //     stride s in {1,2,4} with w + s - 1 <= Lmin.  Every occurrence starting at p then contains the
 //     w-byte window at a = ceil(p/s)*s, which equals bytes [d, d+w) of its pattern with d = a-p < s.
-//     All s*K such pattern windows are hashed into a bitmap of 2^B bits that lives in SHARED MEMORY
-//     (up to 128 KB of the SM's 227 KB); the hot loop hashes the text window at every multiple of s
-//     and tests one bit.  Text is streamed exactly once with coalesced 16-byte loads.
-//   * EXACT WINDOW TABLE (L2-resident, open addressing) maps a window value that passed the bitmap to
-//     its list of (pattern, d) pairs — this kills bitmap false positives in ~one L2 load;
+//     All s*K such pattern windows are hashed into a table that lives in SHARED MEMORY (up to 192 KB of
+//     the SM's 227 KB); the hot loop hashes the text window at every multiple of s and tests one bit.
+//     Text is streamed exactly once with coalesced 16-byte loads.
+//       Lmin >= 6 : k_ac_tri4 — stride 4, the window is ONE aligned text word (see the TRI4 section):
+//                   4 lookups per 16 bytes, candidates queued per warp and verified in batches;
+//       Lmin  = 5 : k_ac_scan<2> — stride 2, paired lookups sharing one shared-memory load;
+//       Lmin <= 4 : k_ac_scan<1> — stride 1.
+//   * EXACT TABLE (L2-resident, open addressing): a window (k_ac_scan) or 6-byte prefix (k_ac_tri4) that
+//     passed the filter is looked up exactly — this kills filter false positives in ~one L2 load;
 //   * VERIFY compares the whole pattern at p = a - d under the exact per-byte case mask, applies the
 //     whole-word test against the global text, shard ownership by start offset, and emits one key
 //     (end << 24 | (1023 - (len-1)) << 14 | pattern_index) whose ascending order is
@@ -72,7 +76,7 @@ struct AcDev
     uint32_t whole_word, want_positions;
     uint32_t zero; // always 0; opaque to the compiler (see the software pipeline in k_ac_scan)
     uint32_t cls_mask, cls_val; // tri4: bits on which ALL pattern trigrams agree — a text word that differs there skips its lookup
-    uint32_t pf_dist, pf_mode; // tri4: L2 prefetch distance in tiles (0 = off); 0 = one bulk prefetch per CTA tile, 1 = per warp vector
+    uint32_t pf_dist; // tri4: L2 prefetch distance in tiles (0 = off)
 };
 
 static constexpr uint32_t HC1 = 0x9E3779B1u, HC2 = 0x85EBCA77u;
@@ -1109,7 +1113,6 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
             threads = e && atoi(e) == 768 ? 768 : 640;
         }
         A.pf_dist = (uint32_t)pf_dist;
-        A.pf_mode = 1;
         const uint64_t full_groups = a.avail_len / 16; // a lookup only needs its own aligned word
         A.tail_a = full_groups * 16;
         A.group_begin = a.own_begin / 16;
