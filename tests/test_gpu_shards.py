@@ -164,3 +164,69 @@ def test_count_lines_on_the_device(func, algo, pats, opts):
         finally:
             p.struct.ac_trie = None
             L.krep_b200_plan_destroy(plan)
+
+
+def test_properties_at_baseline_size_10gib():
+    """BASELINE configs[1] and [3] at their full single-GPU size (10 GiB resident): size-independent properties.
+    Literal: strict sortedness, every reported offset holds the needle, every intact plant is reported, count-only ==
+    list length, 4-shard decomposition == single shard.  Pattern set: every reported (start, end) spells a pattern of
+    the set, and the count equals the SUM of the single-literal counts of all 1000 patterns (the reference's own
+    AC == sum-of-BMH check, test/test_multiple_patterns.c:345-466, at full size)."""
+    import bench
+    L = lib.load()
+    n = 10 * (1 << 30)
+    wl = bench.WORKLOADS["literal8"]
+    spec = lib.make_spec(bench.SEED, bench.PLANT_SEED, wl["period"], wl["needle"], wl["flags"])
+    dev = gu.device_corpus(spec, 0, n)
+    needle = wl["needle"]
+    p = Params(needle)
+    plan = L.krep_b200_plan_create(p.ref(), ALGO_SSE42)
+    try:
+        out = gu.scan(plan, dev, n)
+        cnt, pos = gu.collect(plan, p, out)
+        assert cnt == len(pos) == n // wl["period"]          # one plant per period, none lost, no accidental 8-byte hit
+        starts = torch.tensor([s for s, _ in pos], dtype=torch.int64, device="cuda")
+        assert bool((starts[1:] > starts[:-1]).all())
+        idx = starts[:, None] + torch.arange(len(needle), device="cuda")[None, :]
+        assert bool((dev[idx] == torch.tensor(list(needle), dtype=torch.uint8, device="cuda")[None, :]).all())
+        assert gu.scan(plan, dev, n, want_positions=False).count == cnt
+        merged, q = [], n // 4
+        for g in range(4):
+            b, e = g * q, (g + 1) * q if g < 3 else n
+            o = gu.scan(plan, dev, min(e + 16, n), own_begin=b, own_end=e)
+            c, ps = gu.collect(plan, p, o)
+            merged += ps
+        assert merged == pos
+    finally:
+        L.krep_b200_plan_destroy(plan)
+    del dev
+    torch.cuda.empty_cache()
+
+    wl = bench.WORKLOADS["multi1000"]
+    pats = bench.multi_patterns(wl["multi"], wl["needle"])
+    spec = lib.make_spec(bench.SEED, bench.PLANT_SEED, wl["period"], wl["needle"], wl["flags"])
+    dev = gu.device_corpus(spec, 0, n)
+    pm = Params(pats)
+    pm.struct.ac_trie = 1
+    plan = L.krep_b200_plan_create(pm.ref(), ALGO_AC)
+    try:
+        out = gu.scan(plan, dev, n)
+        cnt, pos = gu.collect(plan, pm, out)
+        assert cnt == len(pos) >= n // wl["period"]
+        pset = set(pats)
+        starts = torch.tensor([s for s, _ in pos], dtype=torch.int64, device="cuda")
+        win = dev[starts[:, None] + torch.arange(12, device="cuda")[None, :]].cpu().numpy()
+        for (s, e), row in zip(pos, win):
+            assert bytes(row[: e - s]) in pset, (s, e)
+        ends = [e for _, e in pos]
+        assert ends == sorted(ends)                           # emission order: ascending end offset
+        total = 0
+        for k, pat in enumerate(pats):
+            pk = Params(pat)
+            plk = L.krep_b200_plan_create(pk.ref(), ALGO_BMH)
+            total += gu.scan(plk, dev, n, want_positions=False).count
+            L.krep_b200_plan_destroy(plk)
+        assert total == cnt                                   # AC == sum over patterns of the single-literal counts
+    finally:
+        pm.struct.ac_trie = None
+        L.krep_b200_plan_destroy(plan)
