@@ -205,6 +205,14 @@ __device__ __noinline__ unsigned slow_window4(const LitDevParams &p, uint64_t gr
     return n;
 }
 
+// Main loads of the window kernel: the sector that holds a warp's "next word" is touched twice (once as lane 31's
+// next-word load, once as the following warp's vector), so these loads keep the default L2 policy instead of
+// evict-first; KREP_B200_W4_CS=1 at build time restores the streaming hint for comparison.
+#ifdef KREP_B200_W4_CS
+#define WLOAD(q) ld_stream(q)
+#else
+#define WLOAD(q) __ldg(q)
+#endif
 template <bool FOLD, bool MASKED, int UNROLL>
 __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ LitDevParams p)
 {
@@ -223,7 +231,7 @@ __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ 
         for (int u = 0; u < UNROLL; u++)
         {
             const uint4 *q = t4 + g0 + (uint64_t)u * blockDim.x + threadIdx.x;
-            v[u] = ld_stream(q);
+            v[u] = WLOAD(q);
             nx[u] = __ldg(reinterpret_cast<const uint32_t *>(q + 1)); // first word of the next vector (L1/L2 hit)
         }
         uint32_t hm = 0; // bit u: vector u holds a candidate
