@@ -118,6 +118,13 @@ uint64_t krep_b200_aho_corasick_search(const search_params_t *, const char *, si
 /* the ARM build's kernel; never chosen by krep_b200_select_search_algorithm (which stands in for the x86 AVX2 build) */
 uint64_t krep_b200_neon_search(const search_params_t *, const char *, size_t, match_result_t *);          /* krep.c:4506 */
 
+/* Many texts, one launch — what search_directory_recursive (krep.c:3310) calling search_file once per small file
+ * becomes when the per-call copy and launch latency matters.  `entry` is one of the ten functions above; text i gets
+ * exactly the count (counts[i]) and positions (results[i], may be NULL, or results == NULL) that
+ * entry(params, texts[i], lens[i], results[i]) would have produced.  Returns 0, or a negative error. */
+int krep_b200_search_batch(search_func_t entry, const search_params_t *params, const char *const *texts,
+                           const size_t *lens, size_t n_texts, uint64_t *counts, match_result_t *const *results);
+
 /* krep.c:1771 — same decision order (regex excluded: returns NULL for
  * use_regex, the caller keeps its own regex_search), same globals. The
  * returned pointer is one of the eight functions above. */

@@ -113,6 +113,7 @@ void engine_shutdown()
     cudaFree(E.d_sort_tmp);
     cudaFree(E.d_bounds);
     cudaFreeHost(E.h_bounds);
+    cudaFreeHost(E.h_batch);
     cudaFree(E.d_counter);
     cudaFree(E.d_text);
     cudaFreeHost(E.h_counter);

@@ -28,6 +28,8 @@ struct Engine
     uint64_t bounds_cap = 0;
     uint64_t *h_bounds = nullptr; // pinned
     uint64_t h_bounds_cap = 0;
+    uint8_t *h_batch = nullptr; // pinned: texts of one krep_b200_search_batch call, packed
+    uint64_t h_batch_cap = 0;
     // host-text entry points: device copy of the caller's buffer + pinned staging ring + key readback
     uint8_t *d_text = nullptr;
     uint64_t text_cap = 0;

@@ -354,27 +354,28 @@ static uint64_t limited_count(int algo, const search_params_t *P, uint64_t total
     }
 }
 
-static uint64_t run_search(int entry_algo, const search_params_t *P, const char *text, size_t n, match_result_t *res)
+// The early returns every reference kernel takes before it looks at the text.  Returns true when the call is already
+// answered (*ret); otherwise *algo is the kernel whose policy applies (precondition fallbacks resolved).
+static bool early_answer(int entry_algo, const search_params_t *P, const char *text, size_t n, match_result_t *res, int *algo_out,
+                         uint64_t *ret)
 {
-    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
-    clear_error();
-    if (!P) return 0;
-    const bool only_matching = g_only_matching;
+    *ret = 0;
     int algo = entry_algo;
     size_t m = 0;
     if (algo == KREP_B200_ALGO_AC)
     {
-        if (!P->ac_trie || !text) return 0;  // aho_corasick.c:306
-        if (P->max_count == 0) return 0;     // aho_corasick.c:316
-        if (n == 0)                          // aho_corasick.c:442-463
+        if (!P->ac_trie || !text) return true;  // aho_corasick.c:306
+        if (P->max_count == 0) return true;     // aho_corasick.c:316
+        if (n == 0)                             // aho_corasick.c:442-463
         {
             for (size_t k = 0; k < P->num_patterns; k++)
                 if (P->pattern_lens[k] == 0)
                 {
                     if (P->track_positions && res) result_push(res, 0, 0);
-                    return 1;
+                    *ret = 1;
+                    return true;
                 }
-            return 0;
+            return true;
         }
     }
     else
@@ -384,29 +385,42 @@ static uint64_t run_search(int entry_algo, const search_params_t *P, const char 
         switch (algo)
         {
         case KREP_B200_ALGO_KMP:
-            if (P->max_count == 0) return 0;
-            if (m == 0 || n < m) return 0;
+            if (P->max_count == 0) return true;
+            if (m == 0 || n < m) return true;
             break;
         case KREP_B200_ALGO_MEMCHR:
-            if (P->max_count == 0 || n == 0) return 0;
+            if (P->max_count == 0 || n == 0) return true;
             m = 1;
             break;
         case KREP_B200_ALGO_MEMCHR_SHORT:
-            if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
-            if (m < 2 || m > 3 || n < m) return 0;
+            if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return true;
+            if (m < 2 || m > 3 || n < m) return true;
             break;
-        default: // BMH, SSE42 and the long simd entries
-            if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return 0;
-            if (m == 0 || n < m) return 0;
+        default: // BMH, SSE42, the long simd entries, NEON
+            if (P->max_count == 0 && (P->count_lines_mode || P->track_positions)) return true;
+            if (m == 0 || n < m) return true;
             break;
         }
-        if (!P->pattern) return 0;
+        if (!P->pattern) return true;
         if (m > 1024)
         {
             set_error(-3, "pattern longer than 1024 bytes (MAX_PATTERN_LENGTH, krep.c:77)");
-            return 0;
+            return true;
         }
     }
+    *algo_out = algo;
+    return false;
+}
+
+static uint64_t run_search(int entry_algo, const search_params_t *P, const char *text, size_t n, match_result_t *res)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    clear_error();
+    if (!P) return 0;
+    const bool only_matching = g_only_matching;
+    int algo = entry_algo;
+    uint64_t early = 0;
+    if (early_answer(entry_algo, P, text, n, res, &algo, &early)) return early;
     if (!engine_ok()) return 0;
     Plan *plan = cached_plan(P, algo, only_matching);
     if (!plan) return 0;
@@ -421,6 +435,98 @@ static uint64_t run_search(int entry_algo, const search_params_t *P, const char 
     Replay r{keys, (size_t)so.stored, text, n, 0};
     if (plan->is_ac) return replay_ac(P, r, res);
     return replay_literal(algo, P, only_matching, plan->m, r, res);
+}
+
+// Many texts, one launch (small files lose to launch and copy latency one by one).  The texts are packed
+// into one pinned buffer at 16-byte aligned offsets, separated by zero gaps longer than the longest pattern, copied and
+// scanned as ONE shard; the sorted occurrence list is then cut per text — an occurrence belongs to a text only if it
+// lies wholly inside it — and each cut is replayed exactly as a separate call would have been (same early returns, own
+// -m limit, own line context).  A gap byte is 0, i.e. not a word character: -w sees a text boundary there, as it should.
+static int run_batch(int entry_algo, const search_params_t *P, const char *const *texts, const size_t *lens, size_t nt,
+                     uint64_t *counts, match_result_t *const *results)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    clear_error();
+    if (!P || !texts || !lens || !counts)
+    {
+        set_error(-3, "krep_b200_search_batch: null argument");
+        return -3;
+    }
+    const bool only_matching = g_only_matching;
+    std::vector<int> algo_of(nt, -1);
+    int algo = -1;
+    for (size_t f = 0; f < nt; f++)
+    {
+        int a = entry_algo;
+        uint64_t early = 0;
+        counts[f] = 0;
+        if (early_answer(entry_algo, P, texts[f], lens[f], results ? results[f] : nullptr, &a, &early)) counts[f] = early;
+        else algo_of[f] = algo = a; // the resolved kernel depends on params only, except for the n < m early return above
+    }
+    if (krep_b200_last_error() != 0) return -3;
+    if (algo < 0) return 0; // every text was answered by an early return
+    if (!engine_ok()) return -1;
+    Plan *plan = cached_plan(P, algo, only_matching);
+    if (!plan) return -2;
+    const size_t gap = (size_t)(plan->is_ac ? plan->max_len : plan->m) + 16;
+    std::vector<uint64_t> off(nt, 0);
+    uint64_t total = 0;
+    for (size_t f = 0; f < nt; f++)
+        if (algo_of[f] >= 0)
+        {
+            off[f] = total;
+            total = (total + lens[f] + gap + 15) & ~15ull;
+        }
+    Engine &E = engine();
+    if (total > E.h_batch_cap)
+    {
+        cudaFreeHost(E.h_batch);
+        E.h_batch = nullptr;
+        E.h_batch_cap = 0;
+        CKH(cudaMallocHost(&E.h_batch, total + total / 4 + 4096));
+        E.h_batch_cap = total + total / 4 + 4096;
+    }
+    memset(E.h_batch, 0, total);
+    for (size_t f = 0; f < nt; f++)
+        if (algo_of[f] >= 0) memcpy(E.h_batch + off[f], texts[f], lens[f]);
+    ScanOut so;
+    if (stage_and_scan(plan, (const char *)E.h_batch, total, 1, &so) != 0) return -2;
+    const uint64_t *keys = nullptr;
+    if (fetch_keys(so, &keys) != 0) return -2;
+    // cut the list per text (texts are in ascending offset order; keys ascend by start, or by end for pattern sets)
+    std::vector<uint64_t> mine;
+    size_t j = 0;
+    for (size_t f = 0; f < nt; f++)
+    {
+        if (algo_of[f] < 0) continue;
+        const uint64_t lo = off[f], hi = off[f] + lens[f];
+        mine.clear();
+        auto span = [&](uint64_t key, uint64_t *s, uint64_t *e) {
+            if (plan->is_ac)
+            {
+                *e = key >> AC_END_SHIFT;
+                *s = *e - (1024 - ((key >> AC_LEN_SHIFT) & 1023));
+            }
+            else
+            {
+                *s = key >> LIT_TAG_BITS;
+                *e = *s + ((key >> 2) & 1 ? plan->m : plan->emit_len);
+            }
+        };
+        while (j < so.stored)
+        {
+            uint64_t s, e;
+            span(keys[j], &s, &e);
+            const uint64_t ord = plan->is_ac ? e : s; // the coordinate the list is sorted by
+            if (ord >= hi + (plan->is_ac ? gap : 0)) break; // belongs to a later text
+            if (s >= lo && e <= hi) mine.push_back(keys[j]);
+            j++;
+        }
+        Replay r{mine.data(), mine.size(), texts[f], lens[f], lo};
+        match_result_t *res = results ? results[f] : nullptr;
+        counts[f] = plan->is_ac ? replay_ac(P, r, res) : replay_literal(algo, P, only_matching, plan->m, r, res);
+    }
+    return 0;
 }
 
 } // namespace kb
@@ -469,6 +575,27 @@ uint64_t krep_b200_aho_corasick_search(const search_params_t *p, const char *t, 
 uint64_t krep_b200_neon_search(const search_params_t *p, const char *t, size_t n, match_result_t *r)
 {
     return run_search(KREP_B200_ALGO_NEON, p, t, n, r);
+}
+
+int krep_b200_search_batch(search_func_t entry, const search_params_t *params, const char *const *texts, const size_t *lens,
+                           size_t n_texts, uint64_t *counts, match_result_t *const *results)
+{
+    int algo = -1;
+    if (entry == krep_b200_boyer_moore_search) algo = KREP_B200_ALGO_BMH;
+    else if (entry == krep_b200_kmp_search) algo = KREP_B200_ALGO_KMP;
+    else if (entry == krep_b200_memchr_search) algo = KREP_B200_ALGO_MEMCHR;
+    else if (entry == krep_b200_memchr_short_search) algo = KREP_B200_ALGO_MEMCHR_SHORT;
+    else if (entry == krep_b200_simd_sse42_search) algo = KREP_B200_ALGO_SSE42;
+    else if (entry == krep_b200_simd_avx2_search) algo = KREP_B200_ALGO_AVX2;
+    else if (entry == krep_b200_simd_avx512_search) algo = KREP_B200_ALGO_AVX512;
+    else if (entry == krep_b200_aho_corasick_search) algo = KREP_B200_ALGO_AC;
+    else if (entry == krep_b200_neon_search) algo = KREP_B200_ALGO_NEON;
+    if (algo < 0)
+    {
+        set_error(-3, "krep_b200_search_batch: entry must be one of this library's search_func_t entry points");
+        return -3;
+    }
+    return run_batch(algo, params, texts, lens, n_texts, counts, results);
 }
 
 // krep.c:1873-1914

@@ -80,6 +80,9 @@ def load():
     L.krep_b200_replay_lines.argtypes = [C.c_int, C.POINTER(SearchParams), C.c_bool, C.POINTER(C.c_uint64), C.c_uint64,
                                          C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(MatchResult)]
     L.krep_b200_replay_lines.restype = C.c_uint64
+    L.krep_b200_search_batch.argtypes = [C.c_void_p, C.POINTER(SearchParams), C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t,
+                                         C.POINTER(C.c_uint64), C.POINTER(C.POINTER(MatchResult))]
+    L.krep_b200_search_batch.restype = C.c_int
     L.krep_b200_export_keys.argtypes = [C.POINTER(DeviceResult), C.c_void_p, C.c_uint64, C.c_void_p]
     L.krep_b200_export_keys.restype = C.c_int
     L.krep_b200_last_kernel_ms.restype = C.c_float
@@ -157,3 +160,40 @@ def corpus_host(spec, offset, length):
     if rc != 0:
         raise RuntimeError("corpus_generate_host failed")
     return buf.raw
+
+
+def search_batch(func, params, texts, with_result=True):
+    """krep_b200_search_batch on a list of bytes objects. -> [(count, [(start, end), ...]), ...]"""
+    L = load()
+    L.krep_b200_set_only_matching(bool(params.only_matching))
+    own_trie = False
+    if func == "aho_corasick" and not params.struct.ac_trie:
+        params.struct.ac_trie = L.krep_b200_ac_trie_build(params.ref())
+        own_trie = True
+    n = len(texts)
+    bufs = [C.create_string_buffer(t, max(len(t), 1)) for t in texts]
+    tarr = (C.c_char_p * max(n, 1))(*[C.cast(b, C.c_char_p) for b in bufs])
+    larr = (C.c_size_t * max(n, 1))(*[len(t) for t in texts])
+    counts = (C.c_uint64 * max(n, 1))()
+    res = [L.krep_b200_match_result_init(16) for _ in range(n)] if with_result else []
+    rarr = (C.POINTER(MatchResult) * max(n, 1))(*res) if with_result else None
+    try:
+        entry = C.cast(getattr(L, SEARCH_ENTRIES[func]), C.c_void_p)
+        rc = L.krep_b200_search_batch(entry, params.ref(), tarr, larr, n, counts, rarr)
+        check(L)
+        assert rc == 0, rc
+        out = []
+        for i in range(n):
+            pos = []
+            if with_result:
+                r = res[i].contents
+                pos = [(r.positions[k].start_offset, r.positions[k].end_offset) for k in range(r.count)]
+            out.append((int(counts[i]), pos))
+        return out
+    finally:
+        for r in res:
+            L.krep_b200_match_result_free(r)
+        if own_trie:
+            L.krep_b200_ac_trie_free(params.struct.ac_trie)
+            params.struct.ac_trie = None
+        L.krep_b200_set_only_matching(False)

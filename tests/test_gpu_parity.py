@@ -161,3 +161,40 @@ def test_aho_corasick_shortest_pattern_6_bytes_or_more_aligned_word_filter():
                 text = base[:off] + pat + base[off + len(pat):]
                 got = lib.search("aho_corasick", Params([pat, other]), text)
                 assert got == (1, [(off, off + len(pat))]), (pat, off, got)
+
+
+@pytest.mark.parametrize("func,pats,opts", [
+    ("sse42", [b"needle"], dict()),
+    ("boyer_moore", [b"ab"], dict(whole_word=True)),
+    ("boyer_moore", [b"the"], dict(count=True)),
+    ("boyer_moore", [b"NeEdLe"], dict(case_sensitive=False, max_count=2)),
+    ("kmp", [b"abab"], dict()),
+    ("memchr", [b"x"], dict()),
+    ("memchr_short", [b"ab"], dict(only_matching=True)),
+    ("avx2", [b"the quick Brown fox_1"], dict()),
+    ("neon", [b"quick"], dict(count=True)),
+    ("aho_corasick", [b"needle", b"quick", b"ab", b"fox_1 needle"], dict()),
+    ("aho_corasick", [b"needle", b"haystack"], dict(whole_word=True, max_count=3)),
+    ("boyer_moore", [b"\x00\x00"], dict()),                  # matches the zero gaps between packed texts: must not leak
+])
+def test_batch_of_small_texts_equals_one_call_each(func, pats, opts):
+    """krep_b200_search_batch packs many texts into one launch; every text must get exactly what a call of its own
+    gives — including empty texts, texts shorter than the pattern, matches at the very start / end of a text, -w at
+    the text boundaries, per-text -m and -c."""
+    rng = random.Random(len(func) * 7 + len(pats))
+    texts = []
+    for i in range(160):
+        n = rng.choice([0, 1, 3, 5, 6, 17, 64, 300, 2000, 9000])
+        t = bytearray(_mixed_text(rng, n)) if n else bytearray()
+        if n >= 12 and rng.random() < 0.5:
+            t[:6] = b"needle"
+        if n >= 12 and rng.random() < 0.5:
+            t[-6:] = b"needle"
+        if n >= 4 and rng.random() < 0.2:
+            t[n // 2:n // 2 + 2] = b"\x00\x00"
+        texts.append(bytes(t))
+    chk = {"neon": ou.reference_neon() or ou.port()}.get(func) or checker()
+    got = lib.search_batch(func, Params(pats, **opts), texts)
+    for i, t in enumerate(texts):
+        want = chk.run(func, Params(pats, **opts), t)
+        assert got[i] == want, (func, pats, opts, i, len(t), got[i][0], want[0])
