@@ -486,9 +486,22 @@ static int run_batch(int entry_algo, const search_params_t *P, const char *const
         CKH(cudaMallocHost(&E.h_batch, total + total / 4 + 4096));
         E.h_batch_cap = total + total / 4 + 4096;
     }
-    memset(E.h_batch, 0, total);
-    for (size_t f = 0; f < nt; f++)
-        if (algo_of[f] >= 0) memcpy(E.h_batch + off[f], texts[f], lens[f]);
+    {
+        // pack with the staging threads; only the gaps are zeroed
+        std::vector<size_t> live;
+        for (size_t f = 0; f < nt; f++)
+            if (algo_of[f] >= 0) live.push_back(f);
+        const long nl = (long)live.size();
+        uint8_t *const hb = E.h_batch;
+#pragma omp parallel for num_threads(copy_threads()) schedule(dynamic, 16)
+        for (long i = 0; i < nl; i++)
+        {
+            const size_t f = live[(size_t)i];
+            const uint64_t end = off[f] + lens[f], next = i + 1 < nl ? off[live[(size_t)i + 1]] : total;
+            memcpy(hb + off[f], texts[f], lens[f]);
+            memset(hb + end, 0, next - end);
+        }
+    }
     ScanOut so;
     if (stage_and_scan(plan, (const char *)E.h_batch, total, 1, &so) != 0) return -2;
     const uint64_t *keys = nullptr;
