@@ -287,14 +287,14 @@ def _main(out_stream):
             return
         sample = int(min(args.cpu_sample_gib, args.gib) * GIB)
         r = run_cpu_reference(args.workload, wl, sample, max(args.steps, 1), args.warmup)
-        print(file=out_stream, *[json.dumps({
+        print(json.dumps({
             "impl": "reference", "metric": metric, "value": r["value"], "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "matches_in_sample": r["count"],
-        })])
+        }), file=out_stream)
         return
 
     import torch
