@@ -230,3 +230,44 @@ def test_properties_at_baseline_size_10gib():
     finally:
         pm.struct.ac_trie = None
         L.krep_b200_plan_destroy(plan)
+
+
+def test_shard_larger_than_32gib_pattern_set_and_literal():
+    """A 34 GiB resident shard: offsets beyond 2^35, and the pattern-set kernel's queue entries hold 32-bit relative
+    group indices, so the host splits such a shard into launches of at most 2^31 groups (32 GiB).  The single-shard
+    result must equal the concatenation of three sub-shards' results, and every match must spell a pattern."""
+    import bench
+    L = lib.load()
+    n = 34 * (1 << 30) + 48
+    wl = bench.WORKLOADS["multi1000"]
+    pats = bench.multi_patterns(wl["multi"], wl["needle"])
+    spec = lib.make_spec(bench.SEED, bench.PLANT_SEED, wl["period"], wl["needle"], wl["flags"])
+    dev = gu.device_corpus(spec, 0, n)
+    pm = Params(pats)
+    pm.struct.ac_trie = 1
+    plan = L.krep_b200_plan_create(pm.ref(), ALGO_AC)
+    pl = Params(wl["needle"])
+    plan_lit = L.krep_b200_plan_create(pl.ref(), ALGO_SSE42)
+    try:
+        cnt, pos = gu.collect(plan, pm, gu.scan(plan, dev, n))
+        assert cnt == len(pos) >= n // wl["period"]
+        assert pos[-1][0] > 33 * (1 << 30)
+        merged = []
+        cuts = [0, 12 * (1 << 30), 24 * (1 << 30) + 16, n]
+        for b, e in zip(cuts[:-1], cuts[1:]):
+            o = gu.scan(plan, dev, min(e + 32, n), own_begin=b, own_end=e)
+            merged += gu.collect(plan, pm, o)[1]
+        assert merged == pos
+        pset = set(pats)
+        tail = [p for p in pos if p[0] > 31 * (1 << 30)][:2000]     # beyond the 2^31-group launch boundary
+        starts = torch.tensor([s for s, _ in tail], dtype=torch.int64, device="cuda")
+        win = dev[starts[:, None] + torch.arange(12, device="cuda")[None, :]].cpu().numpy()
+        for (s, e), row in zip(tail, win):
+            assert bytes(row[: e - s]) in pset, (s, e)
+        # the planted needle through the literal kernel: same occurrences as the pattern set reports for it
+        cl, posl = gu.collect(plan_lit, pl, gu.scan(plan_lit, dev, n))
+        assert posl == [p for p in pos if p[1] - p[0] == len(wl["needle"]) and p in set(posl)] and cl >= n // wl["period"]
+    finally:
+        pm.struct.ac_trie = None
+        L.krep_b200_plan_destroy(plan)
+        L.krep_b200_plan_destroy(plan_lit)
