@@ -204,7 +204,7 @@ def run_cpu_reference(wl_name, wl, sample_bytes, steps, warmup, keep_file=False)
         with open(pat_file, "wb") as f:
             f.write(b"\n".join(pats) + b"\n")
     cores = os.cpu_count() or 1
-    times, count = [], None
+    times, count, single = [], None, None
     try:
         if cli:
             cmd = krep_cli_cmd(cli, wl, sample_path, pat_file)
@@ -212,12 +212,32 @@ def run_cpu_reference(wl_name, wl, sample_bytes, steps, warmup, keep_file=False)
                 t0 = time.perf_counter()
                 r = subprocess.run(cmd, capture_output=True, text=True)
                 dt = time.perf_counter() - t0
+                if it == 0 and dt * (warmup + steps - 1) > 150.0 and sample_bytes > (64 << 20):
+                    # keep the whole reference arm within a few minutes whatever the host: shrink the slice
+                    shrink = max(64 << 20, int(sample_bytes * 150.0 / (dt * (warmup + steps - 1))) & ~0xFFFFF)
+                    with open(sample_path, "r+b") as f:
+                        f.truncate(shrink)
+                    sample_bytes = shrink
                 if it >= warmup:
                     times.append(dt)
                 last = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "0"
                 count = int(last.rsplit(":", 1)[-1])
             kind = "reference"
             how = f"stock krep CLI (oracle/_ref/krep, -msse4.2 -mavx2 build) `{' '.join(cmd[1:-1])} FILE`, default threads"
+            # SURVEY §8d also asks for the -t 1 figure: one run on the first 256 MiB of the same file (head -c via a slice file)
+            try:
+                small = min(sample_bytes, 256 << 20)
+                small_path = sample_path + ".t1"
+                with open(sample_path, "rb") as fi, open(small_path, "wb") as fo:
+                    fo.write(fi.read(small))
+                cmd1 = cmd[:1] + ["-t", "1"] + cmd[1:-1] + [small_path]
+                subprocess.run(cmd1, capture_output=True)
+                t0 = time.perf_counter()
+                subprocess.run(cmd1, capture_output=True)
+                single = {"value": small / (time.perf_counter() - t0) / 1e9, "unit": "GB/s", "sample": f"{small >> 20} MiB, -t 1, one run after one warm-up"}
+                os.unlink(small_path)
+            except Exception:  # noqa: BLE001
+                single = None
         else:
             # compiled reference absent: time the scalar oracle port on one core
             sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -240,7 +260,15 @@ def run_cpu_reference(wl_name, wl, sample_bytes, steps, warmup, keep_file=False)
                 if os.path.exists(pth):
                     os.unlink(pth)
     mean = sum(times) / len(times)
-    return dict(value=sample_bytes / mean / 1e9, best=sample_bytes / min(times) / 1e9, unit="GB/s", cores=cores, kind=kind,
+    extra = {}
+    if cli and single:
+        extra["single_thread"] = single
+    try:
+        with open("/proc/cpuinfo") as f:
+            extra["cpu_model"] = next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), None)
+    except OSError:
+        pass
+    return dict(extra, value=sample_bytes / mean / 1e9, best=sample_bytes / min(times) / 1e9, unit="GB/s", cores=cores, kind=kind,
                 sample=f"{sample_bytes / GIB:.2f} GiB slice [0, n) of the same corpus in {shm}; whole-process wall, "
                        f"mean of {len(times)} runs after {warmup} warm-up; {how}",
                 count=count, ms=mean * 1e3)
@@ -291,7 +319,7 @@ def _main(out_stream):
             "impl": "reference", "metric": metric, "value": r["value"], "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "single_thread", "cpu_model") if k in r},
             "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "matches_in_sample": r["count"],
         }), file=out_stream)
@@ -481,7 +509,7 @@ def _main(out_stream):
     if not args.no_cpu and world == 1:
         try:
             r = run_cpu_reference(args.workload, wl, int(min(args.cpu_sample_gib, args.gib) * GIB), 3, 1)
-            out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "single_thread", "cpu_model") if k in r}
             out["cpu_baseline"]["matches_in_sample"] = r["count"]
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"error": str(e)}
