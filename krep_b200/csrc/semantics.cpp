@@ -441,9 +441,53 @@ static uint64_t replay_window(const search_params_t *P, bool only_matching, size
     return cnt;
 }
 
+// The common case needs no cursor logic at all: when no two occurrences in the list overlap, no -m limit is set and
+// lines are not being counted, boyer_moore_search, kmp_search, memchr_search and simd_sse42_search all keep exactly the
+// occurrences that pass -w, in order (their cursors only differ in how far they step INSIDE an occurrence).  One pass
+// validates that, a second one fills the result vector in bulk (grown by the reference's doubling rule, krep.c:175).
+static bool replay_keep_all(int algo, const search_params_t *P, uint32_t m, const Replay &r, match_result_t *res, uint64_t *out)
+{
+    if (P->count_lines_mode || P->max_count != SIZE_MAX) return false;
+    if (algo != KREP_B200_ALGO_BMH && algo != KREP_B200_ALGO_KMP && algo != KREP_B200_ALGO_SSE42 && algo != KREP_B200_ALGO_MEMCHR)
+        return false;
+    uint64_t prev = 0, kept = 0;
+    for (size_t j = 0; j < r.n; j++)
+    {
+        const uint64_t k = r.keys[j], s = k >> LIT_TAG_BITS;
+        if (!(k & 4) || (j && s < prev + m)) return false; // a prefix-only key, or an overlap: full replay
+        prev = s;
+        kept += !P->whole_word || (k & 3) == 3;
+    }
+    *out = kept;
+    if (!(P->track_positions && res) || kept == 0) return true;
+    uint64_t cap = res->capacity ? res->capacity : 16;
+    while (cap < res->count + kept) cap *= 2;
+    if (cap != res->capacity || !res->positions)
+    {
+        match_position_t *np = (match_position_t *)realloc(res->capacity ? res->positions : nullptr, cap * sizeof *np);
+        if (!np) return false; // let the ordinary path report the allocation failure
+        res->positions = np;
+        res->capacity = cap;
+    }
+    match_position_t *o = res->positions + res->count;
+    for (size_t j = 0; j < r.n; j++)
+    {
+        const uint64_t k = r.keys[j];
+        if (P->whole_word && (k & 3) != 3) continue;
+        const size_t s = (size_t)((k >> LIT_TAG_BITS) - r.base);
+        o->start_offset = s;
+        o->end_offset = s + m;
+        o++;
+    }
+    res->count += kept;
+    return true;
+}
+
 uint64_t replay_literal(int algo, const search_params_t *P, bool only_matching, uint32_t m, const Replay &r,
                         match_result_t *res)
 {
+    uint64_t quick = 0;
+    if (replay_keep_all(algo, P, m, r, res, &quick)) return quick;
     Cursor c{r.keys, r.n, 0, r.base, r.text ? nullptr : r.bounds};
     switch (algo)
     {

@@ -65,20 +65,33 @@ class KeyGatherer:
         """Device buffer the rank's sorted keys are written into (row[1:], at most `cap` keys)."""
         return self.row[1:]
 
-    def exchange(self, count):
+    def exchange(self, count, check=True):
         """`count` keys are in key_buffer() (or count > cap and the caller will be told to retry).
-        -> (keys on host as a 1-D int64 tensor on rank 0 else None, counts list, retry flag)."""
+        -> (keys on host as a 1-D int64 tensor on rank 0 else None, counts list or None, retry flag).
+
+        check=True: every rank reads the gathered counts back (one small synchronising copy) so that all ranks agree
+        on growing the capacity.  check=False is for a steady state whose counts are known to fit (e.g. after warm-up
+        steps ran with check=True): ranks other than 0 then issue the collective and return without synchronising, and
+        rank 0 raises if a count does not fit after all."""
         self.row[0] = int(count)
         dist.all_gather(list(self.all.unbind(0)), self.row)
-        self.host_counts.copy_(self.all[:, 0], non_blocking=False)
-        counts = [int(c) for c in self.host_counts.tolist()]
-        if max(counts) > self.cap:
-            cap = self.cap
-            while cap < max(counts):
-                cap *= 2
-            self._alloc(cap * 2)
-            return None, counts, True
-        if self.rank != 0:
-            return None, counts, False
-        self.host.copy_(self.all, non_blocking=False)
+        if check:
+            self.host_counts.copy_(self.all[:, 0], non_blocking=False)
+            counts = [int(c) for c in self.host_counts.tolist()]
+            if max(counts) > self.cap:
+                cap = self.cap
+                while cap < max(counts):
+                    cap *= 2
+                self._alloc(cap * 2)
+                return None, counts, True
+            if self.rank != 0:
+                return None, counts, False
+            self.host.copy_(self.all, non_blocking=False)
+        else:
+            if self.rank != 0:
+                return None, None, False
+            self.host.copy_(self.all, non_blocking=False)   # one copy brings counts and keys
+            counts = [int(c) for c in self.host[:, 0].tolist()]
+            if max(counts) > self.cap:
+                raise RuntimeError(f"KeyGatherer: count {max(counts)} exceeds capacity {self.cap} in an unchecked exchange")
         return torch.cat([self.host[r, 1:1 + c] for r, c in enumerate(counts)]), counts, False

@@ -95,6 +95,12 @@ def worker(rank, world, port, q):
                 if rank == 0 and (counts2 != counts or not torch.equal(allk2, allk)):
                     ok = False
                     q.put(("gatherer mismatch", func, n, world))
+                # steady-state form: no count read-back on ranks != 0 (capacity is known to fit after the call above)
+                gatherer.key_buffer()[: len(keys)] = torch.tensor(keys, dtype=torch.int64)
+                allk3, counts3, _ = gatherer.exchange(len(keys), check=False)
+                if rank == 0 and (counts3 != counts or not torch.equal(allk3, allk)):
+                    ok = False
+                    q.put(("unchecked gatherer mismatch", func, n, world))
                 if rank == 0:
                     p = Params(pats, **opts)
                     if func == "aho_corasick":
