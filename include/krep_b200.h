@@ -223,7 +223,8 @@ int krep_b200_export_keys(const krep_b200_device_result_t *dev, void *d_dst, uin
  * of the most recent krep_b200_scan_shard / search call on this thread,
  * measured with CUDA events on the launching stream (kernel only, no sort). */
 float krep_b200_last_kernel_ms(void);
-/* Number of kernel launches issued by this library since the last reset. */
+/* Number of launches of this library's own (hand-written) kernels since the last reset; the CUB radix-sort
+ * launches behind krep_b200_scan_shard are library code and are not included. */
 uint64_t krep_b200_launch_count(void);
 void krep_b200_reset_launch_count(void);
 
