@@ -55,7 +55,10 @@ def test_reference_build_agrees_with_its_own_vectors():
     if ref is None:
         pytest.skip("compiled reference not available")
     for v in _vectors():
-        cnt, pos = ref.run(v["func"], params_from(v), text_from(v), with_result=v.get("res", False))
+        chk = ou.reference_neon() if v["func"] == "neon" else ref   # neon_search only exists in the NEON build
+        if chk is None:
+            continue
+        cnt, pos = chk.run(v["func"], params_from(v), text_from(v), with_result=v.get("res", False))
         assert cnt == v["expect"], v["src"]
 
 
