@@ -23,8 +23,8 @@ extern "C" {
 #endif
 
 /* ------------------------------------------------------------------------- */
-/* Types restated from krep.h (layout-identical; checked by static asserts   */
-/* in csrc/abi_check.cpp and tests/test_abi.py)                              */
+/* Types restated from krep.h (layout-identical; checked by tests/test_abi.py, */
+/* which also drives the compiled reference with the very same structs)       */
 /* ------------------------------------------------------------------------- */
 #ifndef KREP_H
 
@@ -79,14 +79,24 @@ typedef uint64_t (*search_func_t)(const search_params_t *params,
 /* Lifetime                                                                  */
 /* ------------------------------------------------------------------------- */
 
-/* Bind the calling process to one CUDA device and create the engine context
- * (streams, pinned staging ring, device scratch).  Optional: every entry point
- * initialises lazily on the current device.  Returns 0, or a negative value
- * after printing "krep: ..." to stderr (the reference's error convention,
- * krep.c:1933).  There is no CPU fallback: without a usable sm_100 device every
- * search entry point prints an error and aborts the call with count 0 and
- * krep_b200_last_error() != 0. */
+/* Make `device` the process's primary CUDA device and create its engine context
+ * (streams, result buffers).  Optional: every entry point initialises lazily,
+ * with the calling thread's current device as the primary one.  One process can
+ * drive several devices: host-text searches spread over the devices chosen by
+ * krep_b200_set_devices / KREP_B200_DEVICES (see below), and the resident-shard
+ * API runs each shard on the device that owns its memory.  Returns 0, or a
+ * negative value after printing "krep: ..." to stderr (the reference's error
+ * convention, krep.c:1933).  There is no CPU fallback: without a usable sm_100
+ * device every search entry point prints an error and aborts the call with
+ * count 0 and krep_b200_last_error() != 0. */
 int krep_b200_init(int device);
+int krep_b200_device_count(void);          /* CUDA devices visible to the process */
+/* The devices a search_func_t call spreads the caller's text over — the analogue of krep's thread count
+ * (krep.c:2851-2905 cuts the file into one chunk per pool thread; here into one contiguous range per GPU, each range
+ * streamed over that GPU's own PCIe link and scanned there, per-device occurrence lists merged by key on the host).
+ * devices == NULL or n == 0 restores the default: KREP_B200_DEVICES=<count> from the environment, else one device per
+ * 16 GiB of text (KREP_B200_DEVICE_SHARE_MB), primary device first. */
+void krep_b200_set_devices(const int *devices, int n);
 void krep_b200_shutdown(void);
 int krep_b200_last_error(void);           /* 0 = last call succeeded          */
 const char *krep_b200_last_error_string(void);
@@ -202,10 +212,16 @@ typedef struct
    const uint64_t *d_line_bounds; /* device, 2 words per stored key, only for plans created with count_lines_mode (-c):
                                global offset of the first byte of the occurrence's line, and of the line's newline (or
                                the text length) — find_line_start / find_line_end (krep.c:363, 401) computed on the GPU */
+   int32_t device;          /* CUDA device that holds the lists                                                      */
+   int32_t slot;            /* which of the device's result buffers the scan used                                    */
+   uint64_t serial;         /* scan number on that device: the lists stay valid until the next scan of that device   */
 } krep_b200_device_result_t;
 
-/* Scan one shard on `stream` (cudaStream_t, NULL = engine stream): launches the
- * filter+verify kernel and sorts the occurrence list on the device. For a
+/* Scan one shard on `stream` (cudaStream_t, NULL = engine stream) of the device that owns shard->d_text: launches
+ * the filter+verify kernel and sorts the occurrence list on the device (lists of up to 16 384 occurrences by the
+ * one-CTA finish kernel, which also hands count and list to the host in the scan's single synchronisation; longer
+ * ones by a radix sort that is still running on `stream` when the call returns — krep_b200_collect /
+ * krep_b200_export_* order themselves after it). For a
  * literal plan every key is (global start offset << 3 | tag bits) of one occurrence
  * that passed the plan's -w filter (tags: see csrc/common.h).  For an AC plan every key packs
  * (end_offset << 24 | (1023 - (len-1)) << 10 ... see krep_b200_ac_key_* below) so
@@ -214,10 +230,26 @@ typedef struct
  * Blocks until the count is known. Returns 0 or a negative error. */
 int krep_b200_scan_shard(const krep_b200_plan_t *plan, const krep_b200_shard_t *shard,
                          int want_positions, void *stream, krep_b200_device_result_t *out);
+/* The same scan in two halves: _begin enqueues it and returns a ticket without waiting, _end waits for it.  A host
+ * that has work of its own per scan (rank 0 of a multi-GPU job replaying the previous step's gathered list) does it
+ * between the two.  At most two scans per device may be in flight. */
+int krep_b200_scan_shard_begin(const krep_b200_plan_t *plan, const krep_b200_shard_t *shard,
+                               int want_positions, void *stream, int *ticket);
+int krep_b200_scan_shard_end(int ticket, krep_b200_device_result_t *out);
 
 /* Copy the first min(out->stored, max_keys) sorted keys of a shard result into another device
  * buffer (device-to-device, on `stream`), e.g. a torch tensor that is then gathered with NCCL. */
 int krep_b200_export_keys(const krep_b200_device_result_t *dev, void *d_dst, uint64_t max_keys, void *stream);
+/* The row a multi-GPU host gathers: d_dst[0] = the shard's exact occurrence count, d_dst[1..] = its first
+ * min(stored, max_keys) sorted keys — one device-to-device copy on `stream`. */
+int krep_b200_export_packed(const krep_b200_device_result_t *dev, void *d_dst, uint64_t max_keys, void *stream);
+/* Merge step of a sharded search (krep.c:2928-3004 without its chunk-edge artefacts): n_lists ascending key lists
+ * (one per shard, shards in text order) -> one ascending list in dst (room for the sum of counts; may alias the
+ * first list).  Literal keys (ordered and owned by start offset) are already globally ordered after concatenation;
+ * pattern-set keys are ordered by END offset (aho_corasick.c:353-431) but owned by START offset, so around every cut
+ * a long match owned by the earlier shard can end after a short match owned by the later one — the merge puts them
+ * back into emission order.  Returns the total. */
+uint64_t krep_b200_merge_keys(const uint64_t *const *lists, const uint64_t *counts, uint32_t n_lists, uint64_t *dst);
 
 /* Timing hook for bench.py: device time in milliseconds of the scan kernel(s)
  * of the most recent krep_b200_scan_shard / search call on this thread,
@@ -239,9 +271,7 @@ uint64_t krep_b200_collect(const krep_b200_plan_t *plan, const search_params_t *
 
 /* Policy replay over a caller-supplied, ascending occurrence-key list in HOST memory (what
  * krep_b200_collect does after reading the device list back).  A multi-GPU host gathers the
- * per-shard lists (already globally ordered across ranks), concatenates them and calls
- * this once, which is the analogue of the reference's merge step (krep.c:2928-3004) without its
- * chunk-edge artefacts.  `text` may be NULL unless params->count_lines_mode is set; `text_len` (the length of the
+ * per-shard lists, merges them with krep_b200_merge_keys and calls this once.  `text` may be NULL unless params->count_lines_mode is set; `text_len` (the length of the
  * whole text) may be 0 = unknown, except for the AVX2 / AVX-512 window kernels with needles > 16 bytes, whose tail
  * handling (krep.c:5059, 5260) depends on it.
  * `algo` is a KREP_B200_ALGO_* value; `only_matching` is the -o global to emulate. */

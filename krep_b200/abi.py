@@ -58,6 +58,9 @@ class DeviceResult(C.Structure):  # krep_b200_device_result_t
         ("overflow", C.c_int),
         ("text_len", C.c_uint64),
         ("d_line_bounds", C.c_void_p),
+        ("device", C.c_int32),
+        ("slot", C.c_int32),
+        ("serial", C.c_uint64),
     ]
 
 

@@ -58,7 +58,18 @@ struct LitDevParams
     uint32_t want_positions;
 };
 
-struct AcDevTables; // scan_multi.cu
+struct AcDevTables;  // scan_multi.cu: one device's copy of a pattern set's tables
+struct AcHostTables; // scan_multi.cu: the tables as compiled on the host (uploaded to each device on first use)
+
+static constexpr int MAX_DEV = 16; // CUDA devices one process can drive
+
+// Device-resident half of a plan, one per CUDA device that has run it (uploaded lazily by plan_on_device()).
+struct PlanDev
+{
+    bool ready = false;
+    uint8_t *d_pat_val = nullptr, *d_pat_mask = nullptr; // literal
+    AcDevTables *ac = nullptr;                           // pattern set
+};
 
 struct Plan
 {
@@ -72,7 +83,7 @@ struct Plan
     uint32_t K[4] = {0, 0, 0, 0};
     uint32_t fold = 0xFFFFFFFFu, win_mask = 0xFFFFFFFFu;
     uint32_t whole_word = 0;
-    uint8_t *d_pat_val = nullptr, *d_pat_mask = nullptr;
+    std::vector<uint8_t> h_val, h_msk; // pattern[k] & mask[k], mask[k] (0xDF where case folds, else 0xFF)
     bool border_free = true; // no proper prefix is also a suffix: occurrences cannot overlap
     bool built_only_matching = false; // value of the -o global the plan was compiled for
     bool count_lines = false;         // -c: scan_shard also computes the line bounds of every occurrence on the device
@@ -80,15 +91,14 @@ struct Plan
     std::vector<std::string> patterns;
     std::vector<uint32_t> pat_lens;
     uint32_t min_len = 0, max_len = 0;
-    AcDevTables *ac = nullptr;
+    AcHostTables *ach = nullptr;
     std::string filter_name;
+    PlanDev dev[MAX_DEV];
     uint64_t magic = 0x6b7265705f623230ull; // "krep_b20"
 };
 
 // engine.cu
-struct Engine;
-Engine &engine();
-bool engine_ok();
+struct DevCtx;
 void set_error(int code, const char *fmt, ...);
 void clear_error();
 
@@ -98,6 +108,10 @@ struct ScanOut
     const uint64_t *d_keys = nullptr;
     int overflow = 0;
     const uint64_t *d_bounds = nullptr; // -c plans: 2 words per stored key (line start, line end), see k_line_bounds
+    const uint64_t *h_sorted = nullptr; // host copy of the sorted keys when the list was small enough to come back with the
+                                        // count (k_finish, engine.cu); valid until the next scan on the same device slot
+    int device = 0;
+    uint64_t serial = 0;                // scan number on that device (stale-result detection in krep_b200_collect)
 };
 
 // Line bounds of an occurrence, global offsets: [0] = first byte of its line, [1] = position of the line's '\n' (or
@@ -106,13 +120,15 @@ static constexpr uint64_t LB_SAME_AS_PREV = ~0ull;     // no newline between the
 static constexpr uint64_t LB_SAME_AS_NEXT = ~0ull - 1; // no newline between this occurrence and the next one
 static constexpr uint64_t LB_OUTSIDE_SHARD = ~0ull - 2; // the line continues into a neighbouring shard
 
-// Launch one shard scan on `stream`; appends to the engine's key list (no reset) when append=true.
-int launch_scan(const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream);
+// Launch one shard scan on `stream` of the device context; appends to that device's key list (no counter reset).
+int launch_scan(DevCtx &C, const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream);
 // literal kernels (scan_literal.cu)
-void launch_literal(const Plan *plan, const LitDevParams &p, cudaStream_t s);
+void launch_literal(const Plan *plan, const LitDevParams &p, int sm_count, cudaStream_t s);
 // multi kernels (scan_multi.cu)
-int ac_build_tables(Plan *plan);
-void ac_free_tables(Plan *plan);
+int ac_build_tables(Plan *plan);                 // host side only: filter tables, exact table, pattern pool
+void ac_free_tables(Plan *plan);                 // host tables (device copies are freed by ac_free_device)
+AcDevTables *ac_upload_tables(const Plan *plan); // copies the host tables to the current device; nullptr on CUDA errors
+void ac_free_device(AcDevTables *T);
 struct AcLaunch
 {
     const uint8_t *text;
@@ -123,7 +139,7 @@ struct AcLaunch
     unsigned long long *counter;
     uint32_t whole_word, want_positions;
 };
-void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t s);
+void launch_ac(const Plan *plan, const AcDevTables *T, const AcLaunch &a, int sm_count, cudaStream_t s);
 void count_launch(int n = 1);
 
 // semantics.cpp — reference control flow replayed over the sorted occurrence list

@@ -1,6 +1,8 @@
 // engine.cu — process-wide engine context, plan compilation, shard scan (launch + device sort),
 // synthetic corpus generator, and the device-level half of the C ABI (include/krep_b200.h).
 #include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -45,32 +47,78 @@ void clear_error()
         }                                                                                          \
     } while (0)
 
-static Engine g_engine;
+static DevCtx g_ctx[MAX_DEV];
 static std::recursive_mutex g_mu;
+static std::mutex g_ctx_mu;
+static int g_primary = -1;
+static int g_visible = -1;
 static uint64_t g_launches = 0;
 static thread_local float t_kernel_ms = 0.f;
+static const std::chrono::steady_clock::time_point g_t0 = std::chrono::steady_clock::now();
 
-Engine &engine() { return g_engine; }
 std::recursive_mutex &engine_mutex() { return g_mu; }
-void count_launch(int n) { g_launches += (uint64_t)n; }
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (uint64_t)n, __ATOMIC_RELAXED); }
 void add_kernel_ms(float ms) { t_kernel_ms += ms; }
 void reset_kernel_ms() { t_kernel_ms = 0.f; }
-
-int engine_init(int device)
+float get_kernel_ms() { return t_kernel_ms; }
+void set_kernel_ms(float ms) { t_kernel_ms = ms; }
+void get_error(ErrState *e)
 {
-    Engine &E = g_engine;
-    if (E.ready) return 0;
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0)
+    e->code = t_err;
+    memcpy(e->msg, t_errmsg, sizeof e->msg);
+}
+void adopt_error(const ErrState &e)
+{
+    t_err = e.code;
+    memcpy(t_errmsg, e.msg, sizeof t_errmsg);
+}
+
+void trace(const char *fmt, ...)
+{
+    static const bool on = getenv("KREP_B200_TRACE") != nullptr;
+    if (!on) return;
+    char buf[400];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_t0).count();
+    fprintf(stderr, "[krep_b200 +%.1f ms] %s\n", ms, buf);
+}
+
+int visible_devices()
+{
+    if (g_visible >= 0) return g_visible;
+    int n = 0;
+    trace("cudaGetDeviceCount ...");
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess)
     {
-        set_error(-1, "no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(e));
+        cudaGetLastError();
+        n = 0;
+    }
+    trace("cudaGetDeviceCount -> %d", n);
+    g_visible = n > MAX_DEV ? MAX_DEV : n;
+    return g_visible;
+}
+
+int primary_device()
+{
+    if (g_primary >= 0) return g_primary;
+    if (visible_devices() == 0)
+    {
+        set_error(-1, "no CUDA device available; this engine has no CPU fallback");
         return -1;
     }
-    if (device < 0)
-    {
-        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
-    }
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+    g_primary = d;
+    return d;
+}
+
+static int ctx_create(DevCtx &E, int device)
+{
+    trace("device %d: creating context", device);
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -85,29 +133,57 @@ int engine_init(int device)
     CK(cudaStreamCreateWithFlags(&E.scan_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&E.copy_stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&E.d_counter, 64));
-    CK(cudaMallocHost(&E.h_counter, 64));
-    CK(cudaEventCreate(&E.ev_a));
-    CK(cudaEventCreate(&E.ev_b));
+    CK(cudaMemset(E.d_counter, 0, 64));
+    E.counter_clean = true;
+    for (int s = 0; s < SCAN_SLOTS; s++)
+    {
+        CK(cudaMalloc(&E.d_pack[s], (PACK_KEYS + 1) * sizeof(uint64_t)));
+        CK(cudaHostAlloc(&E.h_pack[s], (PACK_KEYS + 1) * sizeof(uint64_t), cudaHostAllocMapped | cudaHostAllocPortable));
+        E.h_pack[s][0] = 0;
+        CK(cudaEventCreate(&E.ev_a[s]));
+        CK(cudaEventCreate(&E.ev_b[s]));
+    }
+    CK(cudaMalloc(&E.d_line_out, 64));
+    CK(cudaHostAlloc(&E.h_line_out, 64, cudaHostAllocMapped | cudaHostAllocPortable));
     E.ready = true;
+    trace("device %d: context ready (%s, %d SMs)", device, prop.name, E.sm_count);
     return 0;
 }
 
-bool engine_ok()
+DevCtx *ctx_get(int device)
 {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
-    if (g_engine.ready) return true;
-    return engine_init(-1) == 0;
+    if (device < 0 || device >= MAX_DEV || device >= visible_devices())
+    {
+        set_error(-1, visible_devices() == 0 ? "no CUDA device available; this engine has no CPU fallback"
+                                               : "CUDA device %d is not visible to this process",
+                  device);
+        return nullptr;
+    }
+    DevCtx &E = g_ctx[device];
+    if (E.ready)
+    {
+        cudaSetDevice(device);
+        return &E;
+    }
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (!E.ready && ctx_create(E, device) != 0) return nullptr;
+    return &E;
 }
 
-void engine_shutdown()
+DevCtx *ctx_primary()
 {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
-    Engine &E = g_engine;
+    const int d = primary_device();
+    return d < 0 ? nullptr : ctx_get(d);
+}
+
+static std::vector<Plan *> g_all_plans; // every live plan (device copies are released at shutdown)
+static std::mutex g_plans_mu;
+
+static void ctx_destroy(DevCtx &E)
+{
     if (!E.ready) return;
     cudaSetDevice(E.device);
     cudaDeviceSynchronize();
-    for (auto *p : E.plan_cache) plan_free(p);
-    E.plan_cache.clear();
     cudaFree(E.d_keys[0]);
     cudaFree(E.d_keys[1]);
     cudaFree(E.d_sort_tmp);
@@ -115,26 +191,60 @@ void engine_shutdown()
     cudaFreeHost(E.h_bounds);
     cudaFreeHost(E.h_batch);
     cudaFree(E.d_counter);
-    cudaFree(E.d_text);
-    cudaFreeHost(E.h_counter);
+    cudaFree(E.d_ring);
+    cudaFree(E.d_line_recs);
+    cudaFree(E.d_line_out);
+    cudaFreeHost(E.h_line_out);
     cudaFreeHost(E.h_keys);
+    for (int s = 0; s < SCAN_SLOTS; s++)
+    {
+        cudaFree(E.d_pack[s]);
+        cudaFreeHost(E.h_pack[s]);
+        cudaEventDestroy(E.ev_a[s]);
+        cudaEventDestroy(E.ev_b[s]);
+    }
     for (auto &s : E.stage) cudaFreeHost(s.buf);
-    for (auto &s : E.stage) if (s.ev) cudaEventDestroy(s.ev);
+    for (auto &s : E.stage)
+        if (s.ev) cudaEventDestroy(s.ev);
     for (auto ev : E.ev_pool) cudaEventDestroy(ev);
-    cudaEventDestroy(E.ev_a);
-    cudaEventDestroy(E.ev_b);
+    for (auto ev : E.ring_landed) cudaEventDestroy(ev);
+    for (auto ev : E.ring_scanned) cudaEventDestroy(ev);
     cudaStreamDestroy(E.scan_stream);
     cudaStreamDestroy(E.copy_stream);
-    E = Engine();
+    E = DevCtx();
 }
 
-int ensure_keys(uint64_t cap)
+void plan_cache_clear(); // host_api.cu
+
+void engine_shutdown()
 {
-    Engine &E = g_engine;
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    DeviceGuard guard;
+    plan_cache_clear();
+    {
+        std::lock_guard<std::mutex> lp(g_plans_mu);
+        for (Plan *p : g_all_plans) // plans still held by the host keep their host half; device halves go with the contexts
+            for (int d = 0; d < MAX_DEV; d++)
+            {
+                PlanDev &pd = p->dev[d];
+                if (!pd.ready) continue;
+                cudaSetDevice(d);
+                cudaFree(pd.d_pat_val);
+                cudaFree(pd.d_pat_mask);
+                if (pd.ac) ac_free_device(pd.ac);
+                pd = PlanDev();
+            }
+    }
+    for (int d = 0; d < MAX_DEV; d++) ctx_destroy(g_ctx[d]);
+    g_primary = -1;
+}
+
+int ensure_keys(DevCtx &E, uint64_t cap)
+{
     if (cap <= E.key_cap) return 0;
     uint64_t ncap = E.key_cap ? E.key_cap : (1ull << 20);
     while (ncap < cap) ncap *= 2;
-    CK(cudaStreamSynchronize(E.scan_stream));
+    CK(cudaDeviceSynchronize());
     cudaFree(E.d_keys[0]);
     cudaFree(E.d_keys[1]);
     E.d_keys[0] = E.d_keys[1] = nullptr;
@@ -158,11 +268,60 @@ static uint32_t le32(const uint8_t *b, uint32_t n)
 void plan_free(Plan *p)
 {
     if (!p) return;
-    cudaFree(p->d_pat_val);
-    cudaFree(p->d_pat_mask);
-    if (p->ac) ac_free_tables(p);
+    {
+        std::lock_guard<std::mutex> lp(g_plans_mu);
+        for (size_t i = 0; i < g_all_plans.size(); i++)
+            if (g_all_plans[i] == p)
+            {
+                g_all_plans.erase(g_all_plans.begin() + i);
+                break;
+            }
+    }
+    DeviceGuard guard;
+    for (int d = 0; d < MAX_DEV; d++)
+    {
+        PlanDev &pd = p->dev[d];
+        if (!pd.ready) continue;
+        cudaSetDevice(d);
+        cudaFree(pd.d_pat_val);
+        cudaFree(pd.d_pat_mask);
+        if (pd.ac) ac_free_device(pd.ac);
+    }
+    if (p->ach) ac_free_tables(p);
     p->magic = 0;
     delete p;
+}
+
+// The device half of a plan on the context's device: uploaded the first time that device runs the plan.
+const PlanDev *plan_on_device(const Plan *plan, DevCtx &C)
+{
+    static std::mutex mu;
+    PlanDev &pd = const_cast<Plan *>(plan)->dev[C.device];
+    if (pd.ready) return &pd;
+    std::lock_guard<std::mutex> lk(mu);
+    if (pd.ready) return &pd;
+    cudaSetDevice(C.device);
+    if (plan->is_ac)
+    {
+        pd.ac = ac_upload_tables(plan);
+        if (!pd.ac) return nullptr;
+    }
+    else
+    {
+        const size_t m = plan->h_val.size();
+        if (cudaMalloc(&pd.d_pat_val, m) != cudaSuccess || cudaMalloc(&pd.d_pat_mask, m) != cudaSuccess ||
+            cudaMemcpy(pd.d_pat_val, plan->h_val.data(), m, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(pd.d_pat_mask, plan->h_msk.data(), m, cudaMemcpyHostToDevice) != cudaSuccess)
+        {
+            set_error(-2, "CUDA allocation failed while uploading the pattern to device %d", C.device);
+            cudaFree(pd.d_pat_val);
+            cudaFree(pd.d_pat_mask);
+            pd = PlanDev();
+            return nullptr;
+        }
+    }
+    pd.ready = true;
+    return &pd;
 }
 
 static bool border_free(const std::string &s, bool cs)
@@ -216,6 +375,8 @@ Plan *plan_build(const search_params_t *P, int algo, bool only_matching)
             delete pl;
             return nullptr;
         }
+        std::lock_guard<std::mutex> lp(g_plans_mu);
+        g_all_plans.push_back(pl);
         return pl;
     }
     // ---- single literal ----
@@ -244,12 +405,13 @@ Plan *plan_build(const search_params_t *P, int algo, bool only_matching)
             tag = algo == KREP_B200_ALGO_KMP || (algo == KREP_B200_ALGO_SSE42 && !only_matching);
         pl->whole_word = tag ? 2 : 1;
     }
-    std::vector<uint8_t> val(m), msk(m);
+    pl->h_val.resize(m);
+    pl->h_msk.resize(m);
     const uint8_t *pb = (const uint8_t *)pl->pattern.data();
     for (size_t k = 0; k < m; k++)
     {
-        msk[k] = (!pl->case_sensitive && is_alpha_c(pb[k])) ? 0xDF : 0xFF;
-        val[k] = pb[k] & msk[k];
+        pl->h_msk[k] = (!pl->case_sensitive && is_alpha_c(pb[k])) ? 0xDF : 0xFF;
+        pl->h_val[k] = pb[k] & pl->h_msk[k];
     }
     pl->fold = pl->case_sensitive ? 0xFFFFFFFFu : 0xDFDFDFDFu;
     if (pl->emit_len >= 7)
@@ -267,31 +429,32 @@ Plan *plan_build(const search_params_t *P, int algo, bool only_matching)
         pl->K[0] = le32(pb, wl) & pl->fold & pl->win_mask;
         pl->filter_name = pl->case_sensitive ? "window4" : "window4-fold";
     }
-    if (cudaMalloc(&pl->d_pat_val, m) != cudaSuccess || cudaMalloc(&pl->d_pat_mask, m) != cudaSuccess ||
-        cudaMemcpy(pl->d_pat_val, val.data(), m, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(pl->d_pat_mask, msk.data(), m, cudaMemcpyHostToDevice) != cudaSuccess)
-    {
-        set_error(-2, "CUDA allocation failed while compiling the pattern");
-        plan_free(pl);
-        return nullptr;
-    }
+    std::lock_guard<std::mutex> lp(g_plans_mu);
+    g_all_plans.push_back(pl);
     return pl;
 }
 
 // ---------------------------------------------------------------------------------------------
 // shard scan
 // ---------------------------------------------------------------------------------------------
-int launch_scan(const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream)
+int launch_scan(DevCtx &E, const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream)
 {
-    Engine &E = g_engine;
     if (((uintptr_t)sh->d_text & 15) != 0)
     {
         set_error(-3, "shard text pointer must be 16-byte aligned");
         return -3;
     }
+    const PlanDev *pd = plan_on_device(plan, E);
+    if (!pd) return -2;
     uint64_t own_end = sh->own_end < sh->avail_len ? sh->own_end : sh->avail_len;
     if (plan->is_ac)
     {
+        // the key packs (global end offset << 24): 40 bits of offset
+        if (sh->global_offset + sh->avail_len >= (1ull << 40))
+        {
+            set_error(-3, "pattern-set shards must end below 2^40 bytes of global offset (key layout, csrc/common.h)");
+            return -3;
+        }
         AcLaunch a;
         a.text = (const uint8_t *)sh->d_text;
         a.avail_len = sh->avail_len;
@@ -305,7 +468,7 @@ int launch_scan(const Plan *plan, const krep_b200_shard_t *sh, int want_position
         a.counter = E.d_counter;
         a.whole_word = plan->whole_word;
         a.want_positions = (uint32_t)want_positions;
-        launch_ac(plan, a, stream);
+        launch_ac(plan, pd->ac, a, E.sm_count, stream);
         return 0;
     }
     LitDevParams p;
@@ -340,43 +503,98 @@ int launch_scan(const Plan *plan, const krep_b200_shard_t *sh, int want_position
     p.mulc[0] = 1u << 24;
     p.mulc[1] = 1u << 16;
     p.mulc[2] = 1u << 8;
-    p.pat_val = plan->d_pat_val;
-    p.pat_mask = plan->d_pat_mask;
+    p.pat_val = pd->d_pat_val;
+    p.pat_mask = pd->d_pat_mask;
     p.out = E.d_keys[0];
     p.cap = want_positions ? E.key_cap : 0;
     p.counter = E.d_counter;
     p.whole_word = plan->whole_word;
     p.want_positions = (uint32_t)want_positions;
-    launch_literal(plan, p, stream);
+    launch_literal(plan, p, E.sm_count, stream);
     return 0;
 }
 
-int read_counter(cudaStream_t stream, uint64_t *count)
+int reset_counter(DevCtx &E, cudaStream_t stream)
 {
-    Engine &E = g_engine;
-    CK(cudaMemcpyAsync(E.h_counter, E.d_counter, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    *count = *E.h_counter;
+    if (E.counter_clean) return 0;
+    CK(cudaMemsetAsync(E.d_counter, 0, 64, stream));
+    E.counter_clean = true;
     return 0;
 }
 
-int reset_counter(cudaStream_t stream)
+// ---------------------------------------------------------------------------------------------
+// k_finish — the tail of every scan, one CTA: publishes the occurrence count, zeroes the counter for the next scan, and
+// when the list is short (<= PACK_KEYS, the normal case on low-hit-rate corpora: 10 240 occurrences in the 10 GiB
+// benchmark shard) sorts it in shared memory (bitonic, 64-bit keys) and writes it three ways: back in place (the device
+// list later stages read), into d_pack (what a multi-GPU host hands to its gather) and through mapped pinned memory
+// into h_pack, so that count AND sorted occurrences reach the host with the ONE stream synchronisation the scan needs
+// anyway — no CUB launches, no second read-back.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_finish(unsigned long long *counter, uint64_t *keys, uint64_t cap, uint64_t *d_pack,
+                                                 uint64_t *h_pack, int want_sort)
 {
-    CK(cudaMemsetAsync(g_engine.d_counter, 0, 64, stream));
+    extern __shared__ __align__(16) uint64_t s_keys[];
+    const unsigned long long cnt = *counter;
+    __syncthreads(); // every thread has read the count before it is reset
+    if (threadIdx.x == 0)
+    {
+        *counter = 0;
+        d_pack[0] = cnt;
+        h_pack[0] = cnt;
+    }
+    if (!want_sort || cnt == 0 || cnt > PACK_KEYS || cnt > cap) return;
+    const uint32_t n = (uint32_t)cnt;
+    uint32_t N = 2;
+    while (N < n) N <<= 1;
+    for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) s_keys[i] = i < n ? keys[i] : ~0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= N; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1)
+        {
+            for (uint32_t t = threadIdx.x; t < N / 2; t += blockDim.x)
+            {
+                const uint32_t i = 2 * t - (t & (j - 1)); // lower element of pair t at distance j
+                const uint64_t a = s_keys[i], b = s_keys[i + j];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up)
+                {
+                    s_keys[i] = b;
+                    s_keys[i + j] = a;
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    {
+        const uint64_t v = s_keys[i];
+        keys[i] = v;
+        d_pack[1 + i] = v;
+        h_pack[1 + i] = v;
+    }
+}
+
+int finish_scan(DevCtx &E, int slot, int want_sort, cudaStream_t stream)
+{
+    static bool attr_set[MAX_DEV] = {false};
+    const size_t smem = (size_t)PACK_KEYS * sizeof(uint64_t);
+    if (!attr_set[E.device])
+    {
+        CK(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[E.device] = true;
+    }
+    k_finish<<<1, 1024, smem, stream>>>(E.d_counter, E.d_keys[0], E.key_cap, E.d_pack[slot], E.h_pack[slot],
+                                        (want_sort && E.d_keys[0]) ? 1 : 0);
+    CK(cudaGetLastError());
+    count_launch();
+    E.counter_clean = true;
     return 0;
 }
 
 // Sorts the first n keys of d_keys[0]; the sorted list ends up in *sorted (either buffer).
-int sort_keys(uint64_t n, int end_bit, cudaStream_t stream, const uint64_t **sorted)
+int sort_keys(DevCtx &E, uint64_t n, int end_bit, cudaStream_t stream, const uint64_t **sorted)
 {
-    Engine &E = g_engine;
     *sorted = E.d_keys[0];
     if (n < 2) return 0;
-    if (n > (uint64_t)INT32_MAX * 2)
-    {
-        set_error(-3, "occurrence list too long to sort (%llu)", (unsigned long long)n);
-        return -3;
-    }
     cub::DoubleBuffer<uint64_t> db(E.d_keys[0], E.d_keys[1]);
     size_t need = 0;
     CK(cub::DeviceRadixSort::SortKeys(nullptr, need, db, (int64_t)n, 0, end_bit, stream));
@@ -475,10 +693,9 @@ __global__ void __launch_bounds__(256) k_line_bounds(const uint8_t *__restrict__
     }
 }
 
-static int line_bounds(const Plan *plan, const krep_b200_shard_t *sh, const uint64_t *d_sorted, uint64_t n, cudaStream_t stream,
-                       const uint64_t **d_bounds)
+static int line_bounds(DevCtx &E, const Plan *plan, const krep_b200_shard_t *sh, const uint64_t *d_sorted, uint64_t n,
+                       cudaStream_t stream, const uint64_t **d_bounds)
 {
-    Engine &E = g_engine;
     *d_bounds = nullptr;
     if (n == 0) return 0;
     if (2 * n > E.bounds_cap)
@@ -492,55 +709,154 @@ static int line_bounds(const Plan *plan, const krep_b200_shard_t *sh, const uint
         E.bounds_cap = cap;
     }
     const uint64_t threads = n * 32;
+    // a shard that begins right after a newline (or ends right before one) does not cut a line
+    const int has_prev = sh->prev_byte >= 0 && sh->prev_byte != '\n';
+    const int has_next = sh->next_byte >= 0 && sh->next_byte != '\n';
     k_line_bounds<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>((const uint8_t *)sh->d_text, sh->avail_len, sh->global_offset,
-                                                                        d_sorted, n, plan->is_ac ? 1 : 0, sh->prev_byte >= 0,
-                                                                        sh->next_byte >= 0, E.d_bounds);
+                                                                        d_sorted, n, plan->is_ac ? 1 : 0, has_prev, has_next, E.d_bounds);
     CK(cudaGetLastError());
     count_launch();
     *d_bounds = E.d_bounds;
     return 0;
 }
 
-// Full single-shard scan: reset, launch (rerun with a larger list if it overflowed), sort.
-int scan_shard(const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream, ScanOut *out)
+// One shard scan = counter reset (only if the previous scan did not leave it clean), filter+verify kernel, k_finish.
+// scan_begin enqueues all three and returns; scan_end waits for them (the scan's single synchronisation), and only
+// if the list was too long for k_finish runs the radix sort (or, if it overflowed the list, grows it and rescans).
+int scan_begin(DevCtx &E, const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream, int *slot_out)
 {
-    Engine &E = g_engine;
     if (!stream) stream = E.scan_stream;
-    if (want_positions && ensure_keys(1) != 0) return -2;
+    if (want_positions && ensure_keys(E, 1) != 0) return -2;
+    const int slot = E.next_slot;
+    if (E.pend[slot].active)
+    {
+        set_error(-3, "krep_b200_scan_shard_begin: %d scans are already in flight on device %d", SCAN_SLOTS, E.device);
+        return -3;
+    }
+    if (reset_counter(E, stream) != 0) return -2;
+    CK(cudaEventRecord(E.ev_a[slot], stream));
+    int rc = launch_scan(E, plan, sh, want_positions, stream);
+    if (rc != 0) return rc;
+    CK(cudaEventRecord(E.ev_b[slot], stream));
+    CK(cudaGetLastError());
+    if (finish_scan(E, slot, want_positions, stream) != 0) return -2;
+    PendingScan &P = E.pend[slot];
+    P.active = true;
+    P.plan = plan;
+    P.shard = *sh;
+    P.want_positions = want_positions;
+    P.stream = stream;
+    E.next_slot = (slot + 1) % SCAN_SLOTS;
+    *slot_out = slot;
+    return 0;
+}
+
+int scan_end(DevCtx &E, int slot, ScanOut *out)
+{
+    PendingScan &P = E.pend[slot];
+    if (slot < 0 || slot >= SCAN_SLOTS || !P.active)
+    {
+        set_error(-3, "krep_b200_scan_shard_end: no scan in flight in slot %d", slot);
+        return -3;
+    }
+    P.active = false;
+    const Plan *plan = P.plan;
+    const krep_b200_shard_t *sh = &P.shard;
+    cudaStream_t stream = P.stream;
     reset_kernel_ms();
     for (int attempt = 0; attempt < 3; attempt++)
     {
-        if (reset_counter(stream) != 0) return -2;
-        CK(cudaEventRecord(E.ev_a, stream));
-        int rc = launch_scan(plan, sh, want_positions, stream);
-        if (rc != 0) return rc;
-        CK(cudaEventRecord(E.ev_b, stream));
-        CK(cudaGetLastError());
-        uint64_t cnt = 0;
-        if (read_counter(stream, &cnt) != 0) return -2;
+        CK(cudaStreamSynchronize(stream));
+        const uint64_t cnt = E.h_pack[slot][0];
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, E.ev_a, E.ev_b);
+        cudaEventElapsedTime(&ms, E.ev_a[slot], E.ev_b[slot]);
         add_kernel_ms(ms);
+        *out = ScanOut();
         out->count = cnt;
-        out->overflow = 0;
-        if (!want_positions)
-        {
-            out->stored = 0;
-            out->d_keys = nullptr;
-            return 0;
-        }
+        out->device = E.device;
+        out->serial = ++E.serial;
+        E.result_stream = stream;
+        if (!P.want_positions) return 0;
         if (cnt <= E.key_cap)
         {
+            int rc = 0;
             out->stored = cnt;
-            rc = sort_keys(cnt, key_end_bit(plan, sh->global_offset + sh->avail_len), stream, &out->d_keys);
-            if (rc == 0 && plan->count_lines) rc = line_bounds(plan, sh, out->d_keys, cnt, stream, &out->d_bounds);
+            if (cnt <= PACK_KEYS)
+            {
+                out->d_keys = E.d_keys[0];
+                out->h_sorted = E.h_pack[slot] + 1;
+            }
+            else
+                rc = sort_keys(E, cnt, key_end_bit(plan, sh->global_offset + sh->avail_len), stream, &out->d_keys);
+            if (rc == 0 && plan->count_lines) rc = line_bounds(E, plan, sh, out->d_keys, cnt, stream, &out->d_bounds);
             return rc;
         }
+        // the list overflowed (the counter stays exact past capacity): grow it and scan again
         out->overflow = 1;
-        if (ensure_keys(cnt + cnt / 8 + 1024) != 0) return -2;
+        if (ensure_keys(E, cnt + cnt / 8 + 1024) != 0) return -2;
+        if (reset_counter(E, stream) != 0) return -2;
+        CK(cudaEventRecord(E.ev_a[slot], stream));
+        int rc = launch_scan(E, plan, sh, 1, stream);
+        if (rc != 0) return rc;
+        CK(cudaEventRecord(E.ev_b[slot], stream));
+        if (finish_scan(E, slot, 1, stream) != 0) return -2;
     }
     set_error(-4, "occurrence list kept overflowing");
     return -4;
+}
+
+int scan_shard(DevCtx &E, const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream, ScanOut *out)
+{
+    int slot = 0;
+    int rc = scan_begin(E, plan, sh, want_positions, stream, &slot);
+    if (rc != 0) return rc;
+    return scan_end(E, slot, out);
+}
+
+// Sorted keys on the host: already there when they came back packed with the count, else one copy on the stream that
+// produced them (so the copy is ordered after the sort whatever stream the caller scanned on).
+int fetch_keys(DevCtx &E, const ScanOut &so, const uint64_t **h)
+{
+    *h = nullptr;
+    if (so.stored == 0) return 0;
+    if (so.h_sorted)
+    {
+        *h = so.h_sorted;
+        return 0;
+    }
+    if (so.stored > E.h_keys_cap)
+    {
+        cudaFreeHost(E.h_keys);
+        E.h_keys = nullptr;
+        E.h_keys_cap = 0;
+        uint64_t cap = so.stored + so.stored / 4;
+        if (cap < (1u << 16)) cap = 1u << 16;
+        CK(cudaMallocHost(&E.h_keys, cap * sizeof(uint64_t)));
+        E.h_keys_cap = cap;
+    }
+    cudaStream_t s = E.result_stream ? E.result_stream : E.scan_stream;
+    CK(cudaMemcpyAsync(E.h_keys, so.d_keys, so.stored * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *h = E.h_keys;
+    return 0;
+}
+
+// Ascending lists -> one ascending list.  Concatenation first (the common case is already ordered: literal keys of
+// rank-ordered shards), then one in-place merge per list boundary that is out of order.
+uint64_t merge_key_lists(const uint64_t *const *lists, const uint64_t *counts, uint32_t n_lists, uint64_t *dst)
+{
+    uint64_t total = 0;
+    std::vector<uint64_t> cut;
+    for (uint32_t i = 0; i < n_lists; i++)
+    {
+        if (counts[i] == 0) continue;
+        if (dst + total != lists[i]) memmove(dst + total, lists[i], counts[i] * sizeof(uint64_t));
+        cut.push_back(total);
+        total += counts[i];
+    }
+    for (size_t i = 1; i < cut.size(); i++)
+        if (dst[cut[i] - 1] > dst[cut[i]]) std::inplace_merge(dst, dst + cut[i], dst + (i + 1 < cut.size() ? cut[i + 1] : total));
+    return total;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -598,12 +914,25 @@ int krep_b200_init(int device)
 {
     std::lock_guard<std::recursive_mutex> lk(engine_mutex());
     clear_error();
-    return engine_init(device);
+    if (visible_devices() == 0)
+    {
+        set_error(-1, "no CUDA device available; this engine has no CPU fallback");
+        return -1;
+    }
+    if (device < 0)
+    {
+        device = primary_device();
+        if (device < 0) return -1;
+    }
+    if (!ctx_get(device)) return krep_b200_last_error() ? krep_b200_last_error() : -1;
+    g_primary = device;
+    return 0;
 }
 void krep_b200_shutdown(void) { engine_shutdown(); }
 int krep_b200_last_error(void) { return t_err; }
 const char *krep_b200_last_error_string(void) { return t_errmsg; }
-const char *krep_b200_version(void) { return "krep_b200 0.1.0 (sm_100a)"; }
+const char *krep_b200_version(void) { return "krep_b200 0.2.0 (sm_100a)"; }
+int krep_b200_device_count(void) { return visible_devices(); }
 
 float krep_b200_last_kernel_ms(void) { return t_kernel_ms; }
 uint64_t krep_b200_launch_count(void) { return g_launches; }
@@ -613,7 +942,12 @@ krep_b200_plan_t *krep_b200_plan_create(const search_params_t *params, int algo)
 {
     std::lock_guard<std::recursive_mutex> lk(engine_mutex());
     clear_error();
-    if (!engine_ok()) return nullptr;
+    if (!params) return nullptr;
+    if (visible_devices() == 0)
+    {
+        set_error(-1, "no CUDA device available; this engine has no CPU fallback");
+        return nullptr;
+    }
     return reinterpret_cast<krep_b200_plan_t *>(plan_build(params, resolve_algo(params, algo), krep_b200_get_only_matching()));
 }
 void krep_b200_plan_destroy(krep_b200_plan_t *plan)
@@ -626,26 +960,79 @@ const char *krep_b200_plan_filter_name(const krep_b200_plan_t *plan)
     return plan ? reinterpret_cast<const Plan *>(plan)->filter_name.c_str() : "";
 }
 
-int krep_b200_scan_shard(const krep_b200_plan_t *plan, const krep_b200_shard_t *shard, int want_positions,
-                         void *stream, krep_b200_device_result_t *out)
+// the context of the device that owns a device pointer (a single process may hold shards on several GPUs)
+static DevCtx *ctx_of_pointer(const void *d_ptr)
 {
-    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
-    clear_error();
-    if (!engine_ok()) return -1;
-    if (!plan || !shard || !out)
-    {
-        set_error(-3, "krep_b200_scan_shard: null argument");
-        return -3;
-    }
-    ScanOut so;
-    int rc = scan_shard(reinterpret_cast<const Plan *>(plan), shard, want_positions, (cudaStream_t)stream, &so);
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, d_ptr) == cudaSuccess && a.type == cudaMemoryTypeDevice) return ctx_get(a.device);
+    cudaGetLastError();
+    return ctx_primary();
+}
+
+static void fill_result(const ScanOut &so, const krep_b200_shard_t *shard, int slot, krep_b200_device_result_t *out)
+{
     out->count = so.count;
     out->stored = so.stored;
     out->d_keys = so.d_keys;
     out->overflow = so.overflow;
     out->text_len = shard->global_offset + shard->avail_len;
     out->d_line_bounds = so.d_bounds;
+    out->device = so.device;
+    out->slot = slot;
+    out->serial = so.serial;
+}
+
+int krep_b200_scan_shard_begin(const krep_b200_plan_t *plan, const krep_b200_shard_t *shard, int want_positions, void *stream,
+                               int *ticket)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    clear_error();
+    if (!plan || !shard || !ticket)
+    {
+        set_error(-3, "krep_b200_scan_shard_begin: null argument");
+        return -3;
+    }
+    DeviceGuard guard;
+    DevCtx *C = ctx_of_pointer(shard->d_text);
+    if (!C) return -1;
+    int slot = 0;
+    int rc = scan_begin(*C, reinterpret_cast<const Plan *>(plan), shard, want_positions, (cudaStream_t)stream, &slot);
+    *ticket = C->device * SCAN_SLOTS + slot;
     return rc;
+}
+
+int krep_b200_scan_shard_end(int ticket, krep_b200_device_result_t *out)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    clear_error();
+    if (!out || ticket < 0 || ticket >= MAX_DEV * SCAN_SLOTS)
+    {
+        set_error(-3, "krep_b200_scan_shard_end: bad argument");
+        return -3;
+    }
+    DeviceGuard guard;
+    DevCtx *C = ctx_get(ticket / SCAN_SLOTS);
+    if (!C) return -1;
+    const int slot = ticket % SCAN_SLOTS;
+    const krep_b200_shard_t shard = C->pend[slot].shard;
+    ScanOut so;
+    int rc = scan_end(*C, slot, &so);
+    fill_result(so, &shard, slot, out);
+    return rc;
+}
+
+int krep_b200_scan_shard(const krep_b200_plan_t *plan, const krep_b200_shard_t *shard, int want_positions,
+                         void *stream, krep_b200_device_result_t *out)
+{
+    int ticket = 0;
+    int rc = krep_b200_scan_shard_begin(plan, shard, want_positions, stream, &ticket);
+    if (rc != 0) return rc;
+    if (!out)
+    {
+        set_error(-3, "krep_b200_scan_shard: null argument");
+        return -3;
+    }
+    return krep_b200_scan_shard_end(ticket, out);
 }
 
 int krep_b200_export_keys(const krep_b200_device_result_t *dev, void *d_dst, uint64_t max_keys, void *stream)
@@ -655,10 +1042,42 @@ int krep_b200_export_keys(const krep_b200_device_result_t *dev, void *d_dst, uin
     if (!dev || !d_dst) return -3;
     const uint64_t n = dev->stored < max_keys ? dev->stored : max_keys;
     if (n == 0) return 0;
-    cudaStream_t s = stream ? (cudaStream_t)stream : engine().scan_stream;
+    DeviceGuard guard;
+    DevCtx *C = ctx_get(dev->device);
+    if (!C) return -1;
+    cudaStream_t s = stream ? (cudaStream_t)stream : (C->result_stream ? C->result_stream : C->scan_stream);
     CK(cudaMemcpyAsync(d_dst, dev->d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
     if (!stream) CK(cudaStreamSynchronize(s));
     return 0;
+}
+
+// [count, key_0 .. key_{k-1}] with k = min(stored, max_keys) in one device-to-device copy: the row a multi-GPU host
+// hands to its gather (krep_b200/sharding.py).  count is the exact occurrence count even when k < count.
+int krep_b200_export_packed(const krep_b200_device_result_t *dev, void *d_dst, uint64_t max_keys, void *stream)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    clear_error();
+    if (!dev || !d_dst) return -3;
+    DeviceGuard guard;
+    DevCtx *C = ctx_get(dev->device);
+    if (!C) return -1;
+    cudaStream_t s = stream ? (cudaStream_t)stream : (C->result_stream ? C->result_stream : C->scan_stream);
+    const uint64_t n = dev->stored < max_keys ? dev->stored : max_keys;
+    if (dev->serial == C->serial && dev->stored <= PACK_KEYS && dev->slot >= 0 && dev->slot < SCAN_SLOTS)
+        CK(cudaMemcpyAsync(d_dst, C->d_pack[dev->slot], (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    else
+    {
+        CK(cudaMemcpyAsync(d_dst, C->d_pack[dev->slot & (SCAN_SLOTS - 1)], sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+        if (n) CK(cudaMemcpyAsync((uint64_t *)d_dst + 1, dev->d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    }
+    if (!stream) CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+uint64_t krep_b200_merge_keys(const uint64_t *const *lists, const uint64_t *counts, uint32_t n_lists, uint64_t *dst)
+{
+    if (!lists || !counts || !dst) return 0;
+    return merge_key_lists(lists, counts, n_lists, dst);
 }
 
 uint64_t krep_b200_ac_key_end(uint64_t key) { return key >> AC_END_SHIFT; }
@@ -674,7 +1093,9 @@ int krep_b200_corpus_generate(const krep_b200_corpus_spec_t *spec, void *d_dst, 
 {
     std::lock_guard<std::recursive_mutex> lk(engine_mutex());
     clear_error();
-    if (!engine_ok()) return -1;
+    DeviceGuard guard;
+    DevCtx *C = ctx_of_pointer(d_dst);
+    if (!C) return -1;
     CorpusParams c;
     if (corpus_params(spec, &c) != 0) return -3;
     if (global_offset % 16 != 0)
@@ -683,10 +1104,10 @@ int krep_b200_corpus_generate(const krep_b200_corpus_spec_t *spec, void *d_dst, 
         return -3;
     }
     if (len == 0) return 0;
-    cudaStream_t s = stream ? (cudaStream_t)stream : engine().scan_stream;
+    cudaStream_t s = stream ? (cudaStream_t)stream : C->scan_stream;
     const uint64_t groups = (len + 15) / 16;
     uint64_t blocks = (groups + 255) / 256;
-    const uint64_t maxb = (uint64_t)engine().sm_count * 16;
+    const uint64_t maxb = (uint64_t)C->sm_count * 16;
     if (blocks > maxb) blocks = maxb;
     k_corpus<<<(unsigned)blocks, 256, 0, s>>>(c, (uint8_t *)d_dst, global_offset, len);
     CK(cudaGetLastError());

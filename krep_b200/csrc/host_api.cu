@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <omp.h>
+#include <thread>
 #include "common.h"
 #include "engine.h"
 
@@ -50,6 +51,8 @@ int resolve_algo(const search_params_t *P, int algo)
 }
 
 // ---- plan cache ---------------------------------------------------------------------------------
+static std::vector<Plan *> g_plan_cache; // most recent last; plans are device-independent (uploaded per device on use)
+
 static bool plan_matches(const Plan *pl, const search_params_t *P, int algo, bool only_matching)
 {
     if (pl->algo != algo || pl->case_sensitive != P->case_sensitive || pl->count_lines != P->count_lines_mode) return false;
@@ -72,25 +75,40 @@ static bool plan_matches(const Plan *pl, const search_params_t *P, int algo, boo
 
 static Plan *cached_plan(const search_params_t *P, int algo, bool only_matching)
 {
-    Engine &E = engine();
-    for (size_t i = 0; i < E.plan_cache.size(); i++)
-        if (plan_matches(E.plan_cache[i], P, algo, only_matching))
+    for (size_t i = 0; i < g_plan_cache.size(); i++)
+        if (plan_matches(g_plan_cache[i], P, algo, only_matching))
         {
-            Plan *pl = E.plan_cache[i];
-            E.plan_cache.erase(E.plan_cache.begin() + i);
-            E.plan_cache.push_back(pl); // most recent last
+            Plan *pl = g_plan_cache[i];
+            g_plan_cache.erase(g_plan_cache.begin() + i);
+            g_plan_cache.push_back(pl); // most recent last
             return pl;
         }
     Plan *pl = plan_build(P, algo, only_matching);
     if (!pl) return nullptr;
-    if (E.plan_cache.size() >= 16)
+    if (g_plan_cache.size() >= 16)
     {
-        plan_free(E.plan_cache.front());
-        E.plan_cache.erase(E.plan_cache.begin());
+        plan_free(g_plan_cache.front());
+        g_plan_cache.erase(g_plan_cache.begin());
     }
-    E.plan_cache.push_back(pl);
+    g_plan_cache.push_back(pl);
     return pl;
 }
+
+void plan_cache_clear()
+{
+    for (Plan *p : g_plan_cache) plan_free(p);
+    g_plan_cache.clear();
+}
+
+// AC-trie handles given to the host (krep_b200_ac_trie_build) own their plan: they are not part of the cache and live
+// until krep_b200_ac_trie_free.  The magic word sits first so that a foreign pointer (the reference's own ac_trie_t,
+// whose first word is a node pointer) can be told apart by reading 8 bytes.
+struct TrieHandle
+{
+    uint64_t magic;
+    Plan *plan;
+};
+static constexpr uint64_t TRIE_MAGIC = 0x6b7265705f747269ull; // "krep_tri"
 
 // ---- staging: host text -> HBM, overlapped with the scan ----------------------------------------
 #define CKH(call)                                                                                  \
@@ -113,35 +131,39 @@ static size_t env_mb(const char *name, size_t dflt_mb)
     return x > 0 ? (size_t)x << 20 : dflt_mb << 20;
 }
 
-static int ensure_text(uint64_t n)
+// The caller's text streams through a small ring of device buffers (3 slots of one chunk + halo each) instead of
+// being made resident as a whole: HBM use is bounded whatever the file size, nothing proportional to the text is
+// allocated, and a slot is refilled as soon as the scan of its previous occupant has finished.
+static int ensure_ring(DevCtx &E, size_t slot_bytes, int slots)
 {
-    Engine &E = engine();
-    const uint64_t need = ((n + 63) & ~63ull) + 64;
-    if (need <= E.text_cap) return 0;
-    CKH(cudaStreamSynchronize(E.scan_stream));
-    CKH(cudaStreamSynchronize(E.copy_stream));
-    cudaFree(E.d_text);
-    E.d_text = nullptr;
-    E.text_cap = 0;
-    uint64_t cap = need + need / 16; // a little slack so slightly larger files do not reallocate
-    cudaError_t e = cudaMalloc(&E.d_text, cap);
+    slot_bytes = (slot_bytes + 255) & ~(size_t)255;
+    if (E.ring_slot_bytes >= slot_bytes && E.ring_slots >= slots) return 0;
+    CKH(cudaDeviceSynchronize());
+    cudaFree(E.d_ring);
+    E.d_ring = nullptr;
+    E.ring_slot_bytes = 0;
+    E.ring_slots = 0;
+    cudaError_t e = cudaMalloc(&E.d_ring, slot_bytes * slots);
     if (e != cudaSuccess)
     {
-        cap = need;
-        e = cudaMalloc(&E.d_text, cap);
-    }
-    if (e != cudaSuccess)
-    {
-        set_error(-2, "cannot allocate %llu bytes of HBM for the text (%s)", (unsigned long long)cap, cudaGetErrorString(e));
+        set_error(-2, "cannot allocate %zu bytes of HBM for the staging ring (%s)", slot_bytes * slots, cudaGetErrorString(e));
         return -2;
     }
-    E.text_cap = cap;
+    E.ring_slot_bytes = slot_bytes;
+    E.ring_slots = slots;
+    while ((int)E.ring_landed.size() < slots)
+    {
+        cudaEvent_t a, b;
+        CKH(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CKH(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        E.ring_landed.push_back(a);
+        E.ring_scanned.push_back(b);
+    }
     return 0;
 }
 
-static int ensure_stage(size_t bytes, int slots)
+static int ensure_stage(DevCtx &E, size_t bytes, int slots)
 {
-    Engine &E = engine();
     if (E.stage_bytes >= bytes && (int)E.stage.size() >= slots) return 0;
     for (auto &s : E.stage)
     {
@@ -160,9 +182,8 @@ static int ensure_stage(size_t bytes, int slots)
     return 0;
 }
 
-static cudaEvent_t pool_event(size_t idx)
+static cudaEvent_t pool_event(DevCtx &E, size_t idx)
 {
-    Engine &E = engine();
     while (E.ev_pool.size() <= idx)
     {
         cudaEvent_t ev;
@@ -178,7 +199,7 @@ static int copy_threads()
     if (!nt)
     {
         const char *v = getenv("KREP_B200_COPY_THREADS");
-        nt = v ? atoi(v) : 8; // host threads (8 already saturate the PCIe link: 53 GB/s measured; 32+ oversubscribe and halve it) that move the caller's (pageable) text into the pinned staging ring
+        nt = v ? atoi(v) : 8; // host threads per device (8 already saturate one PCIe link: 53 GB/s measured; 32+ oversubscribe and halve it) that move the caller's (pageable) text into the pinned staging ring
         nt = std::max(1, std::min(nt, std::max(1, omp_get_num_procs())));
     }
     return nt;
@@ -212,111 +233,285 @@ static bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
-// Copies text[0..n) into E.d_text and scans it; on return *so describes the sorted device list.
-static int stage_and_scan(const Plan *plan, const char *text, size_t n, int want_positions, ScanOut *so)
+// One device's share of a search call: global bytes [begin, end) of the caller's text (end - begin a multiple of the
+// chunk size except for the last device), streamed chunk by chunk — host (pinned directly, pageable through the pinned
+// staging ring filled by host threads) -> copy stream -> ring slot -> scan stream — every chunk owning the starts in
+// its own bytes and reading `halo` bytes of the next chunk (copied with it: the source is host memory, so overlapping
+// reads cost nothing) and taking its -w context bytes straight from the host text.  All chunk scans of the device
+// append to one occurrence list; k_finish / the radix sort order it.  If the list overflows, it is grown and the
+// range is staged again.
+struct RangeJob
 {
-    Engine &E = engine();
-    if (ensure_text(n) != 0) return -2;
-    if (want_positions && ensure_keys(1) != 0) return -2;
+    DevCtx *C = nullptr;
+    const Plan *plan = nullptr;
+    const char *text = nullptr;
+    size_t n = 0, begin = 0, end = 0, chunk = 0;
+    int want_positions = 0;
+    bool pinned = false;
+    // results
+    int rc = 0;
+    ScanOut so;
+    const uint64_t *h_keys = nullptr;
+    std::vector<uint64_t> own_keys; // copy of the keys when the device's buffers are reused before the merge
+    float kernel_ms = 0.f;
+    ErrState err;
+};
+
+static int stream_range(RangeJob &J)
+{
+    DevCtx &E = *J.C;
+    CKH(cudaSetDevice(E.device));
+    const Plan *plan = J.plan;
+    if (!plan_on_device(plan, E)) return -2;
     const uint32_t halo = (plan->is_ac ? plan->max_len : plan->m) + 1; // occurrence + the byte after it (-w)
-    const bool pinned = is_pinned(text);
-    const size_t chunk = pinned ? env_mb("KREP_B200_CHUNK_MB", 256) : env_mb("KREP_B200_STAGE_MB", 32);
-    krep_b200_shard_t sh;
-    sh.d_text = E.d_text;
-    sh.avail_len = n;
-    sh.own_begin = 0;
-    sh.own_end = n;
-    sh.global_offset = 0;
-    sh.prev_byte = -1;
-    sh.next_byte = -1;
-    if (n <= chunk + halo)
-    {
-        CKH(cudaMemcpyAsync(E.d_text, text, n, cudaMemcpyHostToDevice, E.scan_stream));
-        return scan_shard(plan, &sh, want_positions, E.scan_stream, so);
-    }
-    if (!pinned && ensure_stage(chunk, 3) != 0) return -2;
+    const size_t chunk = J.chunk, n = J.n;
+    const size_t span = J.end - J.begin;
+    const size_t nchunks = (span + chunk - 1) / chunk;
+    const int nslots = nchunks >= 3 ? 3 : (int)std::max<size_t>(nchunks, 1);
+    if (ensure_ring(E, std::min(chunk, span) + halo + 64, nslots) != 0) return -2;
+    if (!J.pinned && ensure_stage(E, std::min(chunk, span) + halo + 64, nslots) != 0) return -2;
+    if (J.want_positions && ensure_keys(E, 1) != 0) return -2;
     reset_kernel_ms();
-    if (reset_counter(E.scan_stream) != 0) return -2;
-    const size_t nchunks = (n + chunk - 1) / chunk;
-    uint64_t scanned_to = 0; // starts < scanned_to are done
-    for (size_t c = 0; c < nchunks; c++)
+    const int slot = 0;
+    for (int attempt = 0; attempt < 3; attempt++)
     {
-        const size_t off = c * chunk, len = std::min(chunk, n - off);
-        if (pinned)
-            CKH(cudaMemcpyAsync(E.d_text + off, text + off, len, cudaMemcpyHostToDevice, E.copy_stream));
-        else
+        if (reset_counter(E, E.scan_stream) != 0) return -2;
+        for (size_t c = 0; c < nchunks; c++)
         {
-            StageSlot &s = E.stage[c % E.stage.size()];
-            if (s.in_flight) CKH(cudaEventSynchronize(s.ev));
-            parallel_copy(s.buf, (const uint8_t *)text + off, len);
-            CKH(cudaMemcpyAsync(E.d_text + off, s.buf, len, cudaMemcpyHostToDevice, E.copy_stream));
-            CKH(cudaEventRecord(s.ev, E.copy_stream));
-            s.in_flight = true;
-        }
-        cudaEvent_t landed = pool_event(3 * c);
-        CKH(cudaEventRecord(landed, E.copy_stream));
-        CKH(cudaStreamWaitEvent(E.scan_stream, landed, 0));
-        const bool last = c + 1 == nchunks;
-        const uint64_t resident = off + len;
-        krep_b200_shard_t part = sh;
-        part.avail_len = last ? n : resident; // never read bytes that have not landed yet
-        part.own_begin = scanned_to;
-        part.own_end = last ? n : (resident > halo ? resident - halo : 0);
-        part.next_byte = -1; // not needed: own_end leaves the following byte inside avail_len
-        if (part.own_end > part.own_begin)
-        {
-            cudaEvent_t a = pool_event(3 * c + 1), b = pool_event(3 * c + 2);
+            const size_t off = J.begin + c * chunk, len = std::min(chunk, J.end - off);
+            const size_t src_len = std::min(len + halo, n - off);
+            const int rs = (int)(c % E.ring_slots);
+            uint8_t *d_slot = E.d_ring + (size_t)rs * E.ring_slot_bytes;
+            if (c >= (size_t)E.ring_slots) CKH(cudaStreamWaitEvent(E.copy_stream, E.ring_scanned[rs], 0));
+            if (J.pinned)
+                CKH(cudaMemcpyAsync(d_slot, J.text + off, src_len, cudaMemcpyHostToDevice, E.copy_stream));
+            else
+            {
+                StageSlot &s = E.stage[c % E.stage.size()];
+                if (s.in_flight) CKH(cudaEventSynchronize(s.ev));
+                parallel_copy(s.buf, (const uint8_t *)J.text + off, src_len);
+                CKH(cudaMemcpyAsync(d_slot, s.buf, src_len, cudaMemcpyHostToDevice, E.copy_stream));
+                CKH(cudaEventRecord(s.ev, E.copy_stream));
+                s.in_flight = true;
+            }
+            CKH(cudaEventRecord(E.ring_landed[rs], E.copy_stream));
+            CKH(cudaStreamWaitEvent(E.scan_stream, E.ring_landed[rs], 0));
+            krep_b200_shard_t part;
+            part.d_text = d_slot;
+            part.avail_len = src_len;
+            part.own_begin = 0;
+            part.own_end = len;
+            part.global_offset = off;
+            part.prev_byte = off > 0 ? (int32_t)(uint8_t)J.text[off - 1] : -1;
+            part.next_byte = off + src_len < n ? (int32_t)(uint8_t)J.text[off + src_len] : -1;
+            cudaEvent_t a = pool_event(E, 2 * c), b = pool_event(E, 2 * c + 1);
             CKH(cudaEventRecord(a, E.scan_stream));
-            int rc = launch_scan(plan, &part, want_positions, E.scan_stream);
+            int rc = launch_scan(E, plan, &part, J.want_positions, E.scan_stream);
             if (rc != 0) return rc;
             CKH(cudaEventRecord(b, E.scan_stream));
-            scanned_to = part.own_end;
+            CKH(cudaEventRecord(E.ring_scanned[rs], E.scan_stream));
         }
+        CKH(cudaGetLastError());
+        if (finish_scan(E, slot, J.want_positions, E.scan_stream) != 0) return -2;
+        CKH(cudaStreamSynchronize(E.scan_stream));
+        for (auto &s : E.stage) s.in_flight = false;
+        for (size_t c = 0; c < nchunks; c++)
+        {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, E.ev_pool[2 * c], E.ev_pool[2 * c + 1]) == cudaSuccess) add_kernel_ms(ms);
+            else cudaGetLastError();
+        }
+        const uint64_t cnt = E.h_pack[slot][0];
+        J.so = ScanOut();
+        J.so.count = cnt;
+        J.so.device = E.device;
+        J.so.serial = ++E.serial;
+        E.result_stream = E.scan_stream;
+        if (!J.want_positions) return 0;
+        if (cnt <= E.key_cap)
+        {
+            J.so.stored = cnt;
+            if (cnt <= PACK_KEYS)
+            {
+                J.so.d_keys = E.d_keys[0];
+                J.so.h_sorted = E.h_pack[slot] + 1;
+                return 0;
+            }
+            return sort_keys(E, cnt, key_end_bit(plan, n), E.scan_stream, &J.so.d_keys);
+        }
+        // list overflowed: grow it and stage the range again (the ring holds only the last chunks)
+        J.so.overflow = 1;
+        if (ensure_keys(E, cnt + cnt / 8 + 1024) != 0) return -2;
+        reset_kernel_ms();
     }
-    CKH(cudaGetLastError());
-    uint64_t cnt = 0;
-    if (read_counter(E.scan_stream, &cnt) != 0) return -2;
-    for (auto &s : E.stage) s.in_flight = false;
-    for (size_t c = 0; c < nchunks; c++)
-    {
-        float ms = 0.f;
-        if (3 * c + 2 < E.ev_pool.size() && cudaEventElapsedTime(&ms, E.ev_pool[3 * c + 1], E.ev_pool[3 * c + 2]) == cudaSuccess)
-            add_kernel_ms(ms);
-        else
-            cudaGetLastError();
-    }
-    so->count = cnt;
-    so->overflow = 0;
-    so->stored = 0;
-    so->d_keys = nullptr;
-    if (!want_positions) return 0;
-    if (cnt > E.key_cap)
-    {
-        // list overflowed: the text is resident now, rescan it in one launch with a large enough list
-        if (ensure_keys(cnt + cnt / 8 + 1024) != 0) return -2;
-        return scan_shard(plan, &sh, want_positions, E.scan_stream, so);
-    }
-    so->stored = cnt;
-    return sort_keys(cnt, key_end_bit(plan, n), E.scan_stream, &so->d_keys);
+    set_error(-4, "occurrence list kept overflowing");
+    return -4;
 }
 
-static int fetch_keys(const ScanOut &so, const uint64_t **h)
+// ---- which devices a host-text call uses --------------------------------------------------------
+static std::vector<int> g_devices; // krep_b200_set_devices; empty = automatic
+
+static std::vector<int> host_devices(size_t n)
 {
-    Engine &E = engine();
-    *h = nullptr;
-    if (so.stored == 0) return 0;
-    if (so.stored > E.h_keys_cap)
+    std::vector<int> out;
+    const int vis = visible_devices();
+    if (vis == 0) return out;
+    if (!g_devices.empty())
     {
-        cudaFreeHost(E.h_keys);
-        E.h_keys = nullptr;
-        E.h_keys_cap = 0;
-        uint64_t cap = std::max<uint64_t>(so.stored + so.stored / 4, 1 << 16);
-        CKH(cudaMallocHost(&E.h_keys, cap * sizeof(uint64_t)));
-        E.h_keys_cap = cap;
+        for (int d : g_devices)
+            if (d >= 0 && d < vis && std::find(out.begin(), out.end(), d) == out.end()) out.push_back(d);
+        if (!out.empty()) return out;
     }
-    CKH(cudaMemcpyAsync(E.h_keys, so.d_keys, so.stored * sizeof(uint64_t), cudaMemcpyDeviceToHost, E.scan_stream));
-    CKH(cudaStreamSynchronize(E.scan_stream));
-    *h = E.h_keys;
+    const int prim = primary_device();
+    if (prim < 0) return out;
+    int want = 1;
+    const char *v = getenv("KREP_B200_DEVICES");
+    if (v && *v && atoi(v) > 0) want = atoi(v);
+    else
+    {
+        // automatic: one more device per KREP_B200_DEVICE_SHARE_MB of text (default 16 GiB) — a context on another GPU
+        // costs more than its PCIe link saves on anything smaller
+        const size_t share = env_mb("KREP_B200_DEVICE_SHARE_MB", 16384);
+        want = (int)std::min<size_t>((n + share - 1) / share, (size_t)vis);
+    }
+    want = std::max(1, std::min(want, vis));
+    out.push_back(prim);
+    for (int d = 0; d < vis && (int)out.size() < want; d++)
+        if (d != prim) out.push_back(d);
+    return out;
+}
+
+// Result of one host-text search over all devices: total count, and (if wanted) the merged sorted key list on the host.
+struct HostScan
+{
+    uint64_t count = 0;
+    const uint64_t *keys = nullptr;
+    uint64_t nkeys = 0;
+    std::vector<uint64_t> merged; // backing store when several devices contributed
+};
+
+static int stage_and_scan(const Plan *plan, const char *text, size_t n, int want_positions, HostScan *hs)
+{
+    const bool pinned = is_pinned(text);
+    const size_t chunk = pinned ? env_mb("KREP_B200_CHUNK_MB", 256) : env_mb("KREP_B200_STAGE_MB", 32);
+    std::vector<int> devs = host_devices(n);
+    if (devs.empty())
+    {
+        set_error(-1, "no CUDA device available; this engine has no CPU fallback");
+        return -1;
+    }
+    const size_t nchunks = std::max<size_t>((n + chunk - 1) / chunk, 1);
+    if (devs.size() > nchunks) devs.resize(nchunks);
+    const size_t D = devs.size();
+    // one contiguous range of chunks per device; KREP_B200_RANGES=<k> cuts the text into more ranges than devices
+    // (a device then takes its ranges one after the other) — used by the tests to drive the cross-range merge on one GPU
+    size_t R = D;
+    if (const char *v = getenv("KREP_B200_RANGES"))
+        if (atoi(v) > 0) R = std::min<size_t>(std::max<size_t>((size_t)atoi(v), D), nchunks);
+    std::vector<RangeJob> jobs(R);
+    const size_t per = (nchunks + R - 1) / R; // chunks per range
+    for (size_t i = 0; i < R; i++)
+    {
+        RangeJob &J = jobs[i];
+        J.plan = plan;
+        J.text = text;
+        J.n = n;
+        J.chunk = chunk;
+        J.begin = std::min(i * per * chunk, n);
+        J.end = std::min((i + 1) * per * chunk, n);
+        J.want_positions = want_positions;
+        J.pinned = pinned;
+    }
+    trace("search: %zu bytes (%s host memory), %zu device(s), %zu range(s), chunk %zu MiB", n, pinned ? "pinned" : "pageable", D, R,
+          chunk >> 20);
+    // contexts are created here, one after the other on the calling thread; the ranges then run on one host thread per
+    // device (on the calling thread when there is only one device)
+    for (size_t i = 0; i < R; i++)
+    {
+        jobs[i].C = ctx_get(devs[i % D]);
+        if (!jobs[i].C) return -1;
+    }
+    auto run_device = [&jobs, D, R](size_t d) {
+        for (size_t i = d; i < R; i += D)
+        {
+            RangeJob &J = jobs[i];
+            J.rc = J.begin < J.end ? stream_range(J) : 0;
+            J.kernel_ms = get_kernel_ms();
+            if (J.rc != 0) break;
+            if (R > D && J.so.stored) // the device's buffers are reused by its next range: keep this range's keys
+            {
+                const uint64_t *k = nullptr;
+                if ((J.rc = fetch_keys(*J.C, J.so, &k)) != 0) break;
+                J.own_keys.assign(k, k + J.so.stored);
+                J.h_keys = J.own_keys.data();
+            }
+        }
+    };
+    if (D == 1)
+    {
+        run_device(0);
+        float ksum = 0.f;
+        for (auto &J : jobs)
+        {
+            if (J.rc != 0) return J.rc;
+            ksum += J.kernel_ms;
+        }
+        set_kernel_ms(ksum);
+    }
+    else
+    {
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < D; d++)
+            th.emplace_back([&jobs, &run_device, d, D, R] {
+                clear_error();
+                run_device(d);
+                for (size_t i = d; i < R; i += D) get_error(&jobs[i].err);
+            });
+        for (auto &t : th) t.join();
+        std::vector<float> kdev(D, 0.f);
+        for (size_t i = 0; i < R; i++)
+        {
+            if (jobs[i].rc != 0)
+            {
+                adopt_error(jobs[i].err);
+                return jobs[i].rc;
+            }
+            kdev[i % D] += jobs[i].kernel_ms;
+        }
+        set_kernel_ms(*std::max_element(kdev.begin(), kdev.end())); // devices scan concurrently: the slowest one's time
+    }
+    hs->count = 0;
+    for (auto &J : jobs) hs->count += J.so.count;
+    hs->keys = nullptr;
+    hs->nkeys = 0;
+    if (!want_positions) return 0;
+    for (auto &J : jobs)
+    {
+        if (J.so.stored == 0 || J.h_keys) continue;
+        cudaSetDevice(J.C->device);
+        if (fetch_keys(*J.C, J.so, &J.h_keys) != 0) return -2;
+    }
+    if (R == 1)
+    {
+        hs->keys = jobs[0].h_keys;
+        hs->nkeys = jobs[0].so.stored;
+        return 0;
+    }
+    // ranges are in text order: literal keys concatenate in order, pattern-set keys (ordered by end, owned by start) need
+    // the merge around each cut
+    std::vector<const uint64_t *> lists;
+    std::vector<uint64_t> counts;
+    uint64_t total = 0;
+    for (auto &J : jobs)
+    {
+        lists.push_back(J.h_keys);
+        counts.push_back(J.so.stored);
+        total += J.so.stored;
+    }
+    hs->merged.resize(total);
+    hs->nkeys = merge_key_lists(lists.data(), counts.data(), (uint32_t)lists.size(), hs->merged.data());
+    hs->keys = hs->merged.data();
+    trace("search: merged %llu keys from %zu ranges", (unsigned long long)hs->nkeys, R);
     return 0;
 }
 
@@ -412,6 +607,18 @@ static bool early_answer(int entry_algo, const search_params_t *P, const char *t
     return false;
 }
 
+// The plan a call runs: the host's own trie handle when it was built by krep_b200_ac_trie_build for these very
+// patterns, else the cache.
+static Plan *plan_for(const search_params_t *P, int algo, bool only_matching)
+{
+    if (algo == KREP_B200_ALGO_AC && P->ac_trie)
+    {
+        const TrieHandle *h = reinterpret_cast<const TrieHandle *>(P->ac_trie);
+        if (h->magic == TRIE_MAGIC && h->plan && plan_matches(h->plan, P, algo, only_matching)) return h->plan;
+    }
+    return cached_plan(P, algo, only_matching);
+}
+
 static uint64_t run_search(int entry_algo, const search_params_t *P, const char *text, size_t n, match_result_t *res)
 {
     std::lock_guard<std::recursive_mutex> lk(engine_mutex());
@@ -421,20 +628,24 @@ static uint64_t run_search(int entry_algo, const search_params_t *P, const char 
     int algo = entry_algo;
     uint64_t early = 0;
     if (early_answer(entry_algo, P, text, n, res, &algo, &early)) return early;
-    if (!engine_ok()) return 0;
-    Plan *plan = cached_plan(P, algo, only_matching);
+    if (visible_devices() == 0)
+    {
+        set_error(-1, "no CUDA device available; this engine has no CPU fallback");
+        return 0;
+    }
+    DeviceGuard guard;
+    Plan *plan = plan_for(P, algo, only_matching);
     if (!plan) return 0;
     const bool want_result = P->track_positions && res;
     const bool need_list = P->count_lines_mode || want_result || !keeps_all(algo, only_matching, P, plan) ||
                            plan->whole_word == 2;
-    ScanOut so;
-    if (stage_and_scan(plan, text, n, need_list ? 1 : 0, &so) != 0) return 0;
-    if (!need_list) return limited_count(algo, P, so.count);
-    const uint64_t *keys = nullptr;
-    if (fetch_keys(so, &keys) != 0) return 0;
-    Replay r{keys, (size_t)so.stored, text, n, 0};
-    if (plan->is_ac) return replay_ac(P, r, res);
-    return replay_literal(algo, P, only_matching, plan->m, r, res);
+    HostScan hs;
+    if (stage_and_scan(plan, text, n, need_list ? 1 : 0, &hs) != 0) return 0;
+    if (!need_list) return limited_count(algo, P, hs.count);
+    Replay r{hs.keys, (size_t)hs.nkeys, text, n, 0};
+    const uint64_t ret = plan->is_ac ? replay_ac(P, r, res) : replay_literal(algo, P, only_matching, plan->m, r, res);
+    trace("search: replay done (%llu)", (unsigned long long)ret);
+    return ret;
 }
 
 // Many texts, one launch (small files lose to launch and copy latency one by one).  The texts are packed
@@ -465,8 +676,10 @@ static int run_batch(int entry_algo, const search_params_t *P, const char *const
     }
     if (krep_b200_last_error() != 0) return -3;
     if (algo < 0) return 0; // every text was answered by an early return
-    if (!engine_ok()) return -1;
-    Plan *plan = cached_plan(P, algo, only_matching);
+    DeviceGuard guard;
+    DevCtx *Cp = ctx_primary();
+    if (!Cp) return -1;
+    Plan *plan = plan_for(P, algo, only_matching);
     if (!plan) return -2;
     const size_t gap = (size_t)(plan->is_ac ? plan->max_len : plan->m) + 16;
     std::vector<uint64_t> off(nt, 0);
@@ -477,7 +690,7 @@ static int run_batch(int entry_algo, const search_params_t *P, const char *const
             off[f] = total;
             total = (total + lens[f] + gap + 15) & ~15ull;
         }
-    Engine &E = engine();
+    DevCtx &E = *Cp;
     if (total > E.h_batch_cap)
     {
         cudaFreeHost(E.h_batch);
@@ -502,10 +715,10 @@ static int run_batch(int entry_algo, const search_params_t *P, const char *const
             memset(hb + end, 0, next - end);
         }
     }
-    ScanOut so;
-    if (stage_and_scan(plan, (const char *)E.h_batch, total, 1, &so) != 0) return -2;
-    const uint64_t *keys = nullptr;
-    if (fetch_keys(so, &keys) != 0) return -2;
+    HostScan hs;
+    if (stage_and_scan(plan, (const char *)E.h_batch, total, 1, &hs) != 0) return -2;
+    const uint64_t *keys = hs.keys;
+    struct { uint64_t stored; } so{hs.nkeys};
     // cut the list per text (texts are in ascending offset order; keys ascend by start, or by end for pattern sets)
     std::vector<uint64_t> mine;
     size_t j = 0;
@@ -677,17 +890,39 @@ ac_trie_t *krep_b200_ac_trie_build(const search_params_t *params)
     std::lock_guard<std::recursive_mutex> lk(engine_mutex());
     clear_error();
     if (!params || params->num_patterns == 0) return NULL; // aho_corasick.c:113
-    if (!engine_ok()) return NULL;
-    return reinterpret_cast<ac_trie_t *>(cached_plan(params, KREP_B200_ALGO_AC, false));
+    if (visible_devices() == 0)
+    {
+        set_error(-1, "no CUDA device available; this engine has no CPU fallback");
+        return NULL;
+    }
+    Plan *pl = plan_build(params, KREP_B200_ALGO_AC, false); // owned by the handle, not by the plan cache
+    if (!pl) return NULL;
+    TrieHandle *h = new TrieHandle{TRIE_MAGIC, pl};
+    return reinterpret_cast<ac_trie_t *>(h);
 }
-void krep_b200_ac_trie_free(ac_trie_t *) { /* plans are owned by the engine's cache */ }
+void krep_b200_ac_trie_free(ac_trie_t *trie)
+{
+    TrieHandle *h = reinterpret_cast<TrieHandle *>(trie);
+    if (!h || h->magic != TRIE_MAGIC) return;
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    plan_free(h->plan);
+    h->magic = 0;
+    delete h;
+}
 bool krep_b200_ac_trie_root_has_outputs(const ac_trie_t *trie)
 {
-    const Plan *pl = reinterpret_cast<const Plan *>(trie);
-    if (!pl || pl->magic != 0x6b7265705f623230ull || !pl->is_ac) return false;
-    for (uint32_t len : pl->pat_lens)
+    const TrieHandle *h = reinterpret_cast<const TrieHandle *>(trie);
+    if (!h || h->magic != TRIE_MAGIC || !h->plan) return false;
+    for (uint32_t len : h->plan->pat_lens)
         if (len == 0) return true; // an empty pattern's index sits on the root (aho_corasick.c:145)
     return false;
+}
+
+void krep_b200_set_devices(const int *devices, int n)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    g_devices.clear();
+    for (int i = 0; devices && i < n; i++) g_devices.push_back(devices[i]);
 }
 
 // ---- match_result helpers (krep.c:139 / 175 / 244 / 256) ----
@@ -772,18 +1007,24 @@ uint64_t krep_b200_collect(const krep_b200_plan_t *plan_, const search_params_t 
         set_error(-3, "krep_b200_collect: -c needs a plan created with count_lines_mode (line bounds are computed by the scan)");
         return 0;
     }
+    if (!dev->stored) return limited_count(plan->algo, P, plan->is_ac || keeps_all(plan->algo, g_only_matching, P, plan) ? dev->count : 0);
+    DeviceGuard guard;
+    DevCtx *Cp = ctx_get(dev->device);
+    if (!Cp) return 0;
+    DevCtx &E = *Cp;
     ScanOut so;
     so.count = dev->count;
     so.stored = dev->stored;
     so.d_keys = dev->d_keys;
+    // the keys came back with the count if the list was short and no later scan has reused the slot
+    if (dev->serial == E.serial && dev->stored <= PACK_KEYS && dev->slot >= 0 && dev->slot < SCAN_SLOTS)
+        so.h_sorted = E.h_pack[dev->slot] + 1;
     const uint64_t *keys = nullptr;
-    if (so.stored && fetch_keys(so, &keys) != 0) return 0;
-    if (!so.stored) return limited_count(plan->algo, P, plan->is_ac || keeps_all(plan->algo, g_only_matching, P, plan) ? so.count : 0);
+    if (fetch_keys(E, so, &keys) != 0) return 0;
     Replay r{keys, (size_t)so.stored, nullptr, dev->text_len ? (size_t)dev->text_len : (SIZE_MAX >> 1), 0};
     if (P->count_lines_mode)
     {
         // read the device-computed line bounds back and resolve the "same line as my neighbour" markers
-        Engine &E = engine();
         const uint64_t nb = 2 * so.stored;
         if (nb > E.h_bounds_cap)
         {
@@ -797,8 +1038,9 @@ uint64_t krep_b200_collect(const krep_b200_plan_t *plan_, const search_params_t 
             }
             E.h_bounds_cap = nb + nb / 4 + 1024;
         }
-        if (cudaMemcpyAsync(E.h_bounds, dev->d_line_bounds, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, E.scan_stream) != cudaSuccess ||
-            cudaStreamSynchronize(E.scan_stream) != cudaSuccess)
+        cudaStream_t st = E.result_stream ? E.result_stream : E.scan_stream; // ordered after the sort and k_line_bounds
+        if (cudaMemcpyAsync(E.h_bounds, dev->d_line_bounds, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
         {
             set_error(-2, "reading line bounds back failed");
             return 0;

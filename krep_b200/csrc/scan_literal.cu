@@ -26,6 +26,7 @@
 //     SURVEY §8 a12), checks shard ownership by start offset and appends one 64-bit key.
 //
 // Algorithmic traffic: 1 byte read per corpus byte (+ 8 B written per occurrence).
+#include <mutex>
 #include "common.h"
 
 namespace kb {
@@ -262,8 +263,7 @@ __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------ launch
-static int g_sm_count = 0;
-static int g_occ[6] = {0, 0, 0, 0, 0, 0};
+static int g_occ[6] = {0, 0, 0, 0, 0, 0}; // identical on every device of the box (all sm_100)
 
 template <typename K>
 static int occupancy(K kernel)
@@ -273,28 +273,25 @@ static int occupancy(K kernel)
     return nb > 0 ? nb : 1;
 }
 
-void launch_literal(const Plan *plan, const LitDevParams &p, cudaStream_t s)
+void launch_literal(const Plan *plan, const LitDevParams &p, int sm_count, cudaStream_t s)
 {
     constexpr int UNROLL = 4;
-    if (!g_sm_count)
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    static std::once_flag once;
+    std::call_once(once, [] {
         g_occ[0] = occupancy(k_lit_aligned4<false, UNROLL>);
         g_occ[1] = occupancy(k_lit_aligned4<true, UNROLL>);
         g_occ[2] = occupancy(k_lit_window4<false, false, UNROLL>);
         g_occ[3] = occupancy(k_lit_window4<true, false, UNROLL>);
         g_occ[4] = occupancy(k_lit_window4<false, true, UNROLL>);
         g_occ[5] = occupancy(k_lit_window4<true, true, UNROLL>);
-    }
+    });
     const uint64_t groups = p.group_end > p.group_begin ? p.group_end - p.group_begin : 0;
     const uint64_t tile = 256ull * UNROLL;
     uint64_t tiles = (groups + tile - 1) / tile;
     if (tiles == 0) tiles = 1; // still need the tail warp
     const bool folded = plan->fold != 0xFFFFFFFFu, masked = plan->win_mask != 0xFFFFFFFFu;
     const int which = plan->filter == FILTER_WINDOW4 ? 2 + (folded ? 1 : 0) + (masked ? 2 : 0) : (folded ? 1 : 0);
-    uint64_t resident = (uint64_t)g_sm_count * g_occ[which];
+    uint64_t resident = (uint64_t)sm_count * g_occ[which];
     const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
     if (which == 2)
         k_lit_window4<false, false, UNROLL><<<grid, 256, 0, s>>>(p);

@@ -54,6 +54,18 @@ struct AcDevTables
     uint32_t cls_mask = 0, cls_val = 0;
 };
 
+// What ac_build_tables compiles on the host; ac_upload_tables copies it to each device that runs the plan.
+struct AcHostTables
+{
+    std::vector<uint32_t> bitmap;
+    std::vector<uint8_t> bitmap2;
+    std::vector<AcSlot> slots;
+    std::vector<uint32_t> list;
+    std::vector<uint8_t> pool_val, pool_mask;
+    std::vector<uint32_t> pat_off, pat_len;
+    AcDevTables proto; // the scalar fields (device pointers null)
+};
+
 struct AcDev
 {
     const uint32_t *bitmap;
@@ -829,21 +841,11 @@ static uint64_t pat_window(const uint8_t *p, uint32_t w, uint32_t fold)
     return ((uint64_t)(hi & fold) << 32) | (lo & fold);
 }
 
-#define CKB(call)                                                            \
-    do                                                                       \
-    {                                                                        \
-        if ((call) != cudaSuccess)                                           \
-        {                                                                    \
-            set_error(-2, "CUDA allocation/copy failed building AC tables"); \
-            ac_free_tables(plan);                                            \
-            return -2;                                                       \
-        }                                                                    \
-    } while (0)
-
 int ac_build_tables(Plan *plan)
 {
-    AcDevTables *T = new AcDevTables();
-    plan->ac = T;
+    AcHostTables *H = new AcHostTables();
+    plan->ach = H;
+    AcDevTables *T = &H->proto;
     const uint32_t K = (uint32_t)plan->patterns.size();
     T->npat = K;
     uint32_t lmin = 0xFFFFFFFFu, lmax = 0;
@@ -1003,28 +1005,18 @@ int ac_build_tables(Plan *plan)
             const uint32_t hsh = (uint32_t)e.key * HC1 + (uint32_t)(e.key >> 32) * HC2;
             b2[hsh >> 12] |= (uint8_t)(1u << ((hsh >> 9) & 7u));
         }
-        CKB(cudaMalloc(&T->d_bitmap2, b2.size()));
-        CKB(cudaMemcpy(T->d_bitmap2, b2.data(), b2.size(), cudaMemcpyHostToDevice));
+        H->bitmap2.swap(b2);
     }
     if (pv.empty()) { pv.push_back(0); pm.push_back(0); }
     if (list.empty()) list.push_back(0);
-    CKB(cudaMalloc(&T->d_bitmap, bitmap.size() * 4));
-    CKB(cudaMalloc(&T->d_slots, slots.size() * sizeof(AcSlot)));
-    CKB(cudaMalloc(&T->d_list, list.size() * 4));
-    CKB(cudaMalloc(&T->d_pool_val, pv.size()));
-    CKB(cudaMalloc(&T->d_pool_mask, pm.size()));
-    CKB(cudaMalloc(&T->d_pat_off, (K ? K : 1) * 4));
-    CKB(cudaMalloc(&T->d_pat_len, (K ? K : 1) * 4));
-    CKB(cudaMemcpy(T->d_bitmap, bitmap.data(), bitmap.size() * 4, cudaMemcpyHostToDevice));
-    CKB(cudaMemcpy(T->d_slots, slots.data(), slots.size() * sizeof(AcSlot), cudaMemcpyHostToDevice));
-    CKB(cudaMemcpy(T->d_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice));
-    CKB(cudaMemcpy(T->d_pool_val, pv.data(), pv.size(), cudaMemcpyHostToDevice));
-    CKB(cudaMemcpy(T->d_pool_mask, pm.data(), pm.size(), cudaMemcpyHostToDevice));
-    if (K)
-    {
-        CKB(cudaMemcpy(T->d_pat_off, off.data(), K * 4, cudaMemcpyHostToDevice));
-        CKB(cudaMemcpy(T->d_pat_len, len.data(), K * 4, cudaMemcpyHostToDevice));
-    }
+    if (off.empty()) { off.push_back(0); len.push_back(0); }
+    H->bitmap.swap(bitmap);
+    H->slots.swap(slots);
+    H->list.swap(list);
+    H->pool_val.swap(pv);
+    H->pool_mask.swap(pm);
+    H->pat_off.swap(off);
+    H->pat_len.swap(len);
     char name[96];
     snprintf(name, sizeof name, "window%u/stride%u%s bitmap %uKB%s", w, s, tri4 ? (quad ? " aligned-word hash" : " tri4+byte-select") : (s == 2 ? " paired" : ""), nby >> 10,
              plan->case_sensitive ? "" : " fold");
@@ -1034,7 +1026,33 @@ int ac_build_tables(Plan *plan)
 
 void ac_free_tables(Plan *plan)
 {
-    AcDevTables *T = plan->ac;
+    delete plan->ach;
+    plan->ach = nullptr;
+}
+
+template <typename T>
+static bool upload(T **dst, const std::vector<T> &src)
+{
+    if (src.empty()) return true;
+    return cudaMalloc(dst, src.size() * sizeof(T)) == cudaSuccess &&
+           cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+AcDevTables *ac_upload_tables(const Plan *plan)
+{
+    const AcHostTables *H = plan->ach;
+    AcDevTables *T = new AcDevTables(H->proto);
+    if (upload(&T->d_bitmap, H->bitmap) && upload(&T->d_bitmap2, H->bitmap2) && upload(&T->d_slots, H->slots) &&
+        upload(&T->d_list, H->list) && upload(&T->d_pool_val, H->pool_val) && upload(&T->d_pool_mask, H->pool_mask) &&
+        upload(&T->d_pat_off, H->pat_off) && upload(&T->d_pat_len, H->pat_len))
+        return T;
+    set_error(-2, "CUDA allocation/copy failed uploading the pattern-set tables");
+    ac_free_device(T);
+    return nullptr;
+}
+
+void ac_free_device(AcDevTables *T)
+{
     if (!T) return;
     cudaFree(T->d_bitmap);
     cudaFree(T->d_bitmap2);
@@ -1045,12 +1063,11 @@ void ac_free_tables(Plan *plan)
     cudaFree(T->d_pat_off);
     cudaFree(T->d_pat_len);
     delete T;
-    plan->ac = nullptr;
 }
 
-void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
+void launch_ac(const Plan *plan, const AcDevTables *T, const AcLaunch &a, int sm_count, cudaStream_t st)
 {
-    const AcDevTables *T = plan->ac;
+    (void)plan;
     AcDev A;
     memset(&A, 0, sizeof A);
     A.bitmap = T->d_bitmap;
@@ -1094,13 +1111,6 @@ void launch_ac(const Plan *plan, const AcLaunch &a, cudaStream_t st)
     if (A.group_end > total_groups) A.group_end = total_groups;
     if (A.group_begin > A.group_end) A.group_begin = A.group_end;
 
-    static int sm_count = 0;
-    if (!sm_count)
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
     if (T->tri4)
     {
         constexpr int UNROLL = 4;

@@ -83,6 +83,16 @@ def load():
     L.krep_b200_search_batch.argtypes = [C.c_void_p, C.POINTER(SearchParams), C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t,
                                          C.POINTER(C.c_uint64), C.POINTER(C.POINTER(MatchResult))]
     L.krep_b200_search_batch.restype = C.c_int
+    L.krep_b200_scan_shard_begin.argtypes = [C.c_void_p, C.POINTER(Shard), C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    L.krep_b200_scan_shard_begin.restype = C.c_int
+    L.krep_b200_scan_shard_end.argtypes = [C.c_int, C.POINTER(DeviceResult)]
+    L.krep_b200_scan_shard_end.restype = C.c_int
+    L.krep_b200_export_packed.argtypes = [C.POINTER(DeviceResult), C.c_void_p, C.c_uint64, C.c_void_p]
+    L.krep_b200_export_packed.restype = C.c_int
+    L.krep_b200_merge_keys.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p]
+    L.krep_b200_merge_keys.restype = C.c_uint64
+    L.krep_b200_set_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
+    L.krep_b200_device_count.restype = C.c_int
     L.krep_b200_export_keys.argtypes = [C.POINTER(DeviceResult), C.c_void_p, C.c_uint64, C.c_void_p]
     L.krep_b200_export_keys.restype = C.c_int
     L.krep_b200_last_kernel_ms.restype = C.c_float

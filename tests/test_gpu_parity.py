@@ -198,3 +198,45 @@ def test_batch_of_small_texts_equals_one_call_each(func, pats, opts):
     for i, t in enumerate(texts):
         want = chk.run(func, Params(pats, **opts), t)
         assert got[i] == want, (func, pats, opts, i, len(t), got[i][0], want[0])
+
+
+def test_long_needles_65_to_1024_bytes():
+    """Needles beyond every SIMD kernel's range (krep.c:77 MAX_PATTERN_LENGTH 1024): boyer_moore_search semantics."""
+    rng = random.Random(77)
+    base = _mixed_text(rng, 600_000)
+    for m in (65, 100, 255, 256, 257, 1000, 1024):
+        s0 = rng.randrange(0, len(base) - m)
+        pat = base[s0:s0 + m]
+        text = bytearray(base)
+        for at in (0, 12345, 300_001, len(base) - m):
+            text[at:at + m] = pat
+        text = bytes(text)
+        for opts in (dict(), dict(case_sensitive=False), dict(count=True), dict(whole_word=True)):
+            got = lib.search("boyer_moore", Params(pat, **opts), text)
+            want = checker().run("boyer_moore", Params(pat, **opts), text)
+            assert got == want and (opts.get("whole_word") or got[0] >= 4), (m, opts, got[0], want[0])
+
+
+def test_ac_trie_handles_own_their_plan():
+    """krep_b200_ac_trie_build hands out an owned handle: building many tries must not invalidate earlier ones
+    (round-1 finding: handles pointed into a 16-entry LRU cache)."""
+    L = lib.load()
+    text = _mixed_text(random.Random(3), 50_000)
+    handles = []
+    for i in range(40):
+        p = Params([b"needle", b"quick", b"pat%04d" % i] + ([b""] if i == 0 else []))
+        h = L.krep_b200_ac_trie_build(p.ref())
+        assert h
+        handles.append((h, p))
+    assert L.krep_b200_ac_trie_root_has_outputs(handles[0][0]) is True
+    assert L.krep_b200_ac_trie_root_has_outputs(handles[1][0]) is False
+    h, p = handles[3]
+    p.struct.ac_trie = h
+    res = L.krep_b200_match_result_init(16)
+    cnt = L.krep_b200_aho_corasick_search(p.ref(), C.cast(C.c_char_p(text), C.c_void_p), len(text), res)
+    lib.check(L)
+    L.krep_b200_match_result_free(res)
+    p.struct.ac_trie = None
+    assert cnt == checker().run("aho_corasick", Params([b"needle", b"quick", b"pat0003"]), text)[0] > 0
+    for h, _ in handles:
+        L.krep_b200_ac_trie_free(h)

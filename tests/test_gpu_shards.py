@@ -271,3 +271,207 @@ def test_shard_larger_than_32gib_pattern_set_and_literal():
         pm.struct.ac_trie = None
         L.krep_b200_plan_destroy(plan)
         L.krep_b200_plan_destroy(plan_lit)
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: cross-shard merge of pattern-set results with the REAL kernels per shard
+# ------------------------------------------------------------------------------------------------
+def _packed_keys(plan, out, cap=1 << 16):
+    """[count, sorted keys] of a shard result, via krep_b200_export_packed (what a multi-GPU host gathers)."""
+    L = lib.load()
+    row = torch.zeros(cap + 1, dtype=torch.int64, device=f"cuda:{out.device}")
+    assert L.krep_b200_export_packed(C.byref(out), row.data_ptr(), cap, None) == 0
+    lib.check(L)
+    host = row.cpu()
+    cnt = int(host[0])
+    assert cnt == out.count and cnt <= cap
+    return host[:cnt + 1].contiguous()
+
+
+def _merge_and_replay(algo, params, rows, text, only_matching=False):
+    from krep_b200 import sharding
+    L = lib.load()
+    cap = max(r.numel() for r in rows)
+    mat = torch.zeros((len(rows), cap), dtype=torch.int64)
+    counts = []
+    for i, r in enumerate(rows):
+        mat[i, : r.numel()] = r
+        counts.append(int(r[0]))
+    merged = sharding.merge_rows(mat, counts)
+    arr = C.cast(merged.data_ptr(), C.POINTER(C.c_uint64))
+    res = L.krep_b200_match_result_init(16)
+    try:
+        cnt = L.krep_b200_replay(algo, params.ref(), only_matching, arr, merged.numel(), text, len(text), res)
+        r = res.contents
+        return int(cnt), [(r.positions[i].start_offset, r.positions[i].end_offset) for i in range(r.count)]
+    finally:
+        L.krep_b200_match_result_free(res)
+
+
+def _bench_pattern_set_with_nested_pairs():
+    """bench.py's 1000-pattern set (config 4) plus, for a few of its long patterns, an inner 6-byte substring as an
+    extra pattern: a long match that starts before a cut then ends AFTER a short match that starts behind the cut."""
+    import bench
+    wl = bench.WORKLOADS["multi1000"]
+    pats = bench.multi_patterns(wl["multi"], wl["needle"])
+    longs = [p for p in pats if len(p) >= 11][:6]
+    extra = [p[3:9] for p in longs] + [longs[0][5:11], longs[0]]          # nested, nested-at-the-end, and a duplicate
+    return wl, pats + extra, longs
+
+
+@pytest.mark.parametrize("nshards", [2, 3, 8])
+def test_pattern_set_shards_merge_equals_reference(nshards):
+    """One corpus cut into 2 / 3 / 8 shards, the real multi-pattern kernel per shard (own buffer, global offset, context
+    bytes), lists merged by key (krep_b200_merge_keys), replayed — must equal the compiled reference's single-chunk
+    aho_corasick_search position for position, in order, with -m 1, -c and -w as well.  Adversarial plants: a long
+    pattern starting 1..9 bytes before every cut with a nested short pattern behind the cut."""
+    L = lib.load()
+    wl, pats, longs = _bench_pattern_set_with_nested_pairs()
+    n = 6 * (1 << 20) + 4242
+    spec = lib.make_spec(77, 78, 1 << 16, wl["needle"], wl["flags"])
+    host = bytearray(lib.corpus_host(spec, 0, n))
+    S = ((n + nshards - 1) // nshards + 15) // 16 * 16
+    for g in range(1, nshards):
+        for k, delta in enumerate((1, 4, 9)):
+            p = longs[(g + k) % len(longs)]
+            s = g * S - delta - k * 40
+            host[s - 1:s + len(p) + 1] = b" " + p + b" "
+    host = bytes(host)
+    halo = max(map(len, pats)) + 1
+    for opts in (dict(), dict(max_count=1), dict(count=True), dict(whole_word=True), dict(case_sensitive=False, max_count=40)):
+        p = Params(pats, **opts)
+        p.struct.ac_trie = 1
+        plan = L.krep_b200_plan_create(p.ref(), ALGO_AC)
+        lib.check(L)
+        try:
+            rows, keep = [], []
+            for g in range(nshards):
+                b, e = g * S, min((g + 1) * S, n)
+                avail = min(e + halo, n)
+                shard = gu.to_device(host[b:avail])
+                keep.append(shard)
+                out = gu.scan(plan, shard, avail - b, own_begin=0, own_end=e - b, global_offset=b,
+                              prev_byte=host[b - 1] if b else -1, next_byte=host[avail] if avail < n else -1)
+                rows.append(_packed_keys(plan, out))
+            cat = torch.cat([r[1:] for r in rows])
+            if not opts:
+                assert not bool((cat[1:] >= cat[:-1]).all()), "plants did not produce an out-of-order concatenation"
+            got = _merge_and_replay(ALGO_AC, p, rows, host)
+            p.struct.ac_trie = None
+            want = checker().run("aho_corasick", Params(pats, **opts), host)
+            assert got == want, (nshards, opts, got[0], want[0])
+            assert want[0] > 0
+        finally:
+            p.struct.ac_trie = None
+            L.krep_b200_plan_destroy(plan)
+
+
+def test_host_search_cut_into_ranges_equals_reference(monkeypatch):
+    """The search_func_t entry points on host text with the text cut into several ranges (one per device, or — here, on
+    one GPU — KREP_B200_RANGES ranges taken one after the other): per-range lists merged by key inside the library."""
+    wl, pats, longs = _bench_pattern_set_with_nested_pairs()
+    n = 7 * (1 << 20) + 999
+    spec = lib.make_spec(79, 80, 1 << 15, wl["needle"], wl["flags"])
+    host = bytearray(lib.corpus_host(spec, 0, n))
+    mb = 1 << 20
+    for c in range(1, 7):
+        for k, delta in enumerate((1, 5, 8)):
+            p = longs[(c + k) % len(longs)]
+            s = c * mb - delta - 30 * k
+            host[s - 1:s + len(p) + 1] = b" " + p + b" "
+    host = bytes(host)
+    monkeypatch.setenv("KREP_B200_STAGE_MB", "1")
+    monkeypatch.setenv("KREP_B200_CHUNK_MB", "1")
+    for ranges in ("1", "3", "7"):
+        monkeypatch.setenv("KREP_B200_RANGES", ranges)
+        for opts in (dict(), dict(max_count=1), dict(count=True), dict(whole_word=True, case_sensitive=False)):
+            got = lib.search("aho_corasick", Params(pats, **opts), host)
+            want = checker().run("aho_corasick", Params(pats, **opts), host)
+            assert got == want, (ranges, opts, got[0], want[0])
+        for func, pat, opts in (("sse42", wl["needle"], {}), ("boyer_moore", b"the", dict(count=True)),
+                                ("boyer_moore", b"et", dict(whole_word=True))):
+            got = lib.search(func, Params(pat, **opts), host)
+            want = checker().run(func, Params(pat, **opts), host)
+            assert got == want, (ranges, func, opts)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_host_search_on_several_devices_equals_reference():
+    """krep_b200_set_devices: one search call, the text spread over every visible GPU (single process)."""
+    L = lib.load()
+    wl, pats, longs = _bench_pattern_set_with_nested_pairs()
+    n = 300 * (1 << 20) + 12345
+    spec = lib.make_spec(81, 82, 1 << 18, wl["needle"], wl["flags"])
+    host = lib.corpus_host(spec, 0, n)
+    ndev = torch.cuda.device_count()
+    devs = (C.c_int * ndev)(*range(ndev))
+    try:
+        L.krep_b200_set_devices(devs, ndev)
+        for func, pp, opts in (("aho_corasick", pats, {}), ("sse42", wl["needle"], {}), ("boyer_moore", b"the", dict(count=True))):
+            got = lib.search(func, Params(pp, **opts), host)
+            L.krep_b200_set_devices(None, 0)
+            one = lib.search(func, Params(pp, **opts), host)
+            L.krep_b200_set_devices(devs, ndev)
+            assert got == one and got[0] > 0, (func, got[0], one[0])
+        small = host[: 9 * (1 << 20)]
+        got = lib.search("aho_corasick", Params(pats), small)
+        assert got == checker().run("aho_corasick", Params(pats), small)
+    finally:
+        L.krep_b200_set_devices(None, 0)
+
+
+def test_scan_begin_end_on_a_user_stream_then_collect():
+    """krep_b200_scan_shard_begin / _end, on a non-default stream: collect must be ordered after the device sort
+    whatever stream the scan ran on (round-1 advisor finding), also for lists longer than the packed read-back."""
+    from krep_b200.abi import DeviceResult, Shard
+    L = lib.load()
+    n = 24 * (1 << 20)
+    spec = lib.make_spec(5, 6, 1 << 9, b"the", 0)          # one plant per 512 B -> ~49 k occurrences (> PACK_KEYS)
+    dev = gu.device_corpus(spec, 0, n)
+    host = bytes(dev[:n].cpu().numpy())
+    st = torch.cuda.Stream()
+    for pat, func, algo in ((b"the", "boyer_moore", ALGO_BMH), (NEEDLE, "sse42", ALGO_SSE42)):
+        p = Params(pat)
+        plan = L.krep_b200_plan_create(p.ref(), algo)
+        try:
+            sh = Shard(dev.data_ptr(), n, 0, n, 0, -1, -1)
+            ticket = C.c_int(-1)
+            assert L.krep_b200_scan_shard_begin(plan, C.byref(sh), 1, C.c_void_p(st.cuda_stream), C.byref(ticket)) == 0
+            out = DeviceResult()
+            assert L.krep_b200_scan_shard_end(ticket.value, C.byref(out)) == 0
+            lib.check(L)
+            got = gu.collect(plan, p, out)
+            want = checker().run(func, Params(pat), host)
+            assert got == want and (got[0] > 16384 or pat == NEEDLE)
+        finally:
+            L.krep_b200_plan_destroy(plan)
+
+
+def test_count_lines_on_newline_aligned_shards():
+    """-c on the device for shards that begin right after a newline and end right before one (prev_byte / next_byte are
+    newlines): no line is cut, so every shard resolves its own line bounds and the line counts add up."""
+    L = lib.load()
+    rng_text = _texts_for_line_counting()[2]
+    cuts = [0]
+    for target in (len(rng_text) // 3, 2 * len(rng_text) // 3):
+        cuts.append(rng_text.index(b"\n", target) + 1)
+    cuts.append(len(rng_text))
+    for pats, func, algo in (([b"needle"], "boyer_moore", ALGO_BMH), ([b"needle", b"quick", b"haystack"], "aho_corasick", ALGO_AC)):
+        p = Params(pats, count=True)
+        if func == "aho_corasick":
+            p.struct.ac_trie = 1
+        plan = L.krep_b200_plan_create(p.ref(), algo)
+        try:
+            total = 0
+            for b, e in zip(cuts[:-1], cuts[1:]):
+                piece = rng_text[b:e - 1] if e < len(rng_text) else rng_text[b:e]   # the shard stops before its final newline
+                devt = gu.to_device(piece)
+                out = gu.scan(plan, devt, len(piece), global_offset=(b + 15) // 16 * 16,
+                              prev_byte=0x0A if b else -1, next_byte=0x0A if e < len(rng_text) else -1)
+                total += gu.collect(plan, p, out)[0]
+            p.struct.ac_trie = None
+            want = checker().run(func, Params(pats, count=True), rng_text)
+            assert total == want[0] > 3, (func, total, want[0])
+        finally:
+            p.struct.ac_trie = None
+            L.krep_b200_plan_destroy(plan)

@@ -26,6 +26,22 @@ def _free_port():
     return p
 
 
+# the verdict's repro: a long pattern that starts just before a shard cut ends AFTER a short pattern that starts behind
+# the cut -> per-rank lists concatenated in rank order are not in aho_corasick_search's emission order (end ascending)
+STRADDLE = b"abcdefghij"
+
+
+def straddle_text(n, world):
+    """n bytes of filler with 'abcdefghij' planted so that it starts 2 bytes before every shard cut."""
+    t = bytearray(b"xy z\n" * (n // 5 + 1))[:n]
+    for r in range(1, world):
+        cut, _, _ = sharding.shard_bounds(n, world, r, 11)
+        for s in (cut - 2, cut - 9):           # straddling the cut; and wholly in the earlier rank's halo region
+            if 0 <= s and s + len(STRADDLE) <= n:
+                t[s:s + len(STRADDLE)] = STRADDLE
+    return bytes(t)
+
+
 CASES = [
     ("sse42", ALGO_SSE42, [b"needle"], dict()),
     ("boyer_moore", ALGO_BMH, [b"abab"], dict()),                       # overlapping occurrences across the cut
@@ -33,6 +49,13 @@ CASES = [
     ("boyer_moore", ALGO_BMH, [b"needle"], dict(whole_word=True)),      # -w context across the cut
     ("boyer_moore", ALGO_BMH, [b"NeEdLe"], dict(case_sensitive=False, max_count=3)),
     ("aho_corasick", ALGO_AC, [b"ab", b"abcdefgh", b"needle", b"dle x"], dict()),   # short pattern inside the halo: no duplicate
+    # nested short pattern behind the cut, long pattern across it (merge by key, not concatenation)
+    ("aho_corasick", ALGO_AC, [STRADDLE, b"cde"], dict(text="straddle")),
+    ("aho_corasick", ALGO_AC, [STRADDLE, b"cde"], dict(text="straddle", max_count=1)),      # -m 1 keeps the FIRST emission
+    ("aho_corasick", ALGO_AC, [STRADDLE, b"cde", b"hij", b"j"], dict(text="straddle", max_count=3)),
+    ("aho_corasick", ALGO_AC, [STRADDLE, b"cde", b"cde", b"efg"], dict(text="straddle")),   # duplicate patterns: one emission per index
+    ("aho_corasick", ALGO_AC, [STRADDLE, b"cde"], dict(text="straddle", count=True)),       # -c
+    ("aho_corasick", ALGO_AC, [b"ABCDEFGHIJ", b"Cde", b"z"], dict(text="straddle", case_sensitive=False, whole_word=True)),
 ]
 
 
@@ -79,29 +102,28 @@ def worker(rank, world, port, q):
     gatherer = sharding.KeyGatherer(world, rank, "cpu", capacity=4)  # tiny: the grow-and-retry path runs too
     try:
         for ci, (func, algo, pats, opts) in enumerate(CASES):
+            opts = dict(opts)
+            kind = opts.pop("text", "words")
             for n in (1000, 4099):
-                text = make_text(100 + ci, n)
+                text = straddle_text(n, world) if kind == "straddle" else make_text(100 + ci, n)
                 halo = max(map(len, pats)) + 1
                 begin, own, avail = sharding.shard_bounds(n, world, rank, halo)
                 keys = shard_keys(func, pats, opts, text, begin, own, avail)
                 allk, counts = sharding.gather_keys(torch.tensor(keys, dtype=torch.int64), world, rank, "cpu")
                 # the single-collective exchange used by bench.py must deliver the same list
-                while True:
-                    if len(keys) <= gatherer.cap:
-                        gatherer.key_buffer()[: len(keys)] = torch.tensor(keys, dtype=torch.int64)
-                    allk2, counts2, retry = gatherer.exchange(len(keys))
-                    if not retry:
-                        break
-                if rank == 0 and (counts2 != counts or not torch.equal(allk2, allk)):
-                    ok = False
-                    q.put(("gatherer mismatch", func, n, world))
-                # steady-state form: no count read-back on ranks != 0 (capacity is known to fit after the call above)
-                gatherer.key_buffer()[: len(keys)] = torch.tensor(keys, dtype=torch.int64)
-                allk3, counts3, _ = gatherer.exchange(len(keys), check=False)
-                if rank == 0 and (counts3 != counts or not torch.equal(allk3, allk)):
-                    ok = False
-                    q.put(("unchecked gatherer mismatch", func, n, world))
+                while not gatherer.negotiate(len(keys)):
+                    pass
+                gatherer.row[0] = len(keys)
+                gatherer.row[1:1 + len(keys)] = torch.tensor(keys, dtype=torch.int64)
+                gatherer.post(ci & 1)
                 if rank == 0:
+                    allk2, counts2 = gatherer.fetch(ci & 1)
+                    if counts2 != counts or not torch.equal(allk2, allk):
+                        ok = False
+                        q.put(("gatherer mismatch", func, n, world))
+                    if allk.numel() > 1 and not bool((allk[1:] >= allk[:-1]).all()):
+                        ok = False
+                        q.put(("merged list not ascending", func, n, world))
                     p = Params(pats, **opts)
                     if func == "aho_corasick":
                         p.struct.ac_trie = 1
@@ -115,11 +137,46 @@ def worker(rank, world, port, q):
                     if got != want:
                         ok = False
                         q.put(("mismatch", func, pats, opts, n, world, got[0], want[0]))
+                    if kind == "straddle" and set(opts) <= {"case_sensitive"} and want[0] < 2:
+                        ok = False
+                        q.put(("straddle case did not produce the nested pair", pats, n, world, want))
     finally:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         q.put(("done", ok))
+
+
+def test_merge_keys_restores_emission_order():
+    """The repro from the round-1 review, without any process group: two shards of a 64-byte text."""
+    text = bytearray(b"." * 64)
+    text[30:40] = STRADDLE                      # starts 2 bytes before the cut at 32
+    text = bytes(text)
+    pats = [STRADDLE, b"cde"]
+    lists = []
+    for rank in range(2):
+        b, own, avail = sharding.shard_bounds(64, 2, rank, 11)
+        lists.append(shard_keys("aho_corasick", pats, {}, text, b, own, avail))
+    assert lists[0] and lists[1] and lists[0][-1] > lists[1][0]          # concatenation is NOT ascending
+    cap = max(map(len, lists))
+    rows = torch.zeros((2, cap + 1), dtype=torch.int64)
+    for r, ks in enumerate(lists):
+        rows[r, 0] = len(ks)
+        rows[r, 1:1 + len(ks)] = torch.tensor(ks, dtype=torch.int64)
+    merged = sharding.merge_rows(rows, [len(x) for x in lists]).tolist()
+    assert merged == sorted(lists[0] + lists[1])
+    L = lib.load()
+    for maxc in (2 ** 64 - 1, 1):
+        p = Params(pats, max_count=maxc)
+        p.struct.ac_trie = 1
+        arr = (C.c_uint64 * len(merged))(*merged)
+        res = L.krep_b200_match_result_init(16)
+        cnt = L.krep_b200_replay(ALGO_AC, p.ref(), False, arr, len(merged), text, len(text), res)
+        got = (int(cnt), [(res.contents.positions[i].start_offset, res.contents.positions[i].end_offset)
+                          for i in range(res.contents.count)])
+        L.krep_b200_match_result_free(res)
+        assert got == ou.port().run("aho_corasick", Params(pats, max_count=maxc), text)
+        assert got[1][0] == (32, 35)            # the short match ends first
 
 
 @pytest.mark.parametrize("world", [2, 3])
