@@ -1,15 +1,21 @@
 #!/usr/bin/env python
 """bench.py — BASELINE.json's metric: GB/s scanned over an HBM-resident synthetic corpus.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--gib G] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--gib G] [--workload NAME] [--no-side]
 
-N=1 workload = BASELINE configs[1]: 8-byte literal over 10 GiB of HBM-resident synthetic ASCII, count + all offsets.
-For N>1 (launched by torchrun, one rank per GPU) each rank holds its own 10 GiB shard (+halo) of an N x 10 GiB
-corpus (weak scaling), scans it, and one NCCL gather brings counts and offsets to rank 0.
+Headline (value / roofline / e2e) = BASELINE configs[1]: 8-byte literal over 10 GiB of HBM-resident synthetic ASCII per
+GPU, count + all offsets.  For N>1 (launched by torchrun, one rank per GPU) each rank holds its own 10 GiB shard
+(+halo) of an N x 10 GiB corpus (weak scaling), scans it, and one NCCL gather brings counts and offsets to rank 0
+(SURVEY §8e), which merges them by key and replays them into krep's match_result_t.
 
-A step = one pass of the hot path over the resident corpus: filter+verify kernel, device sort of the occurrence
-list, read-back, policy replay into krep's match_result_t (+ the gather for N>1).  Inputs are 10 GiB >> 126 MB L2,
-so nothing survives in L2 between steps.  One JSON line on stdout (rank 0).
+The same JSON line carries a `workloads` object with BASELINE configs[2], [3] and [4] at their stated TOTAL sizes,
+sharded over the N GPUs the run was launched with (strong scaling): -i 4-byte literal on 50 GiB, 1000 patterns on
+20 GiB (20 / 10 / 5 / 2.5 GiB per GPU at N = 1 / 2 / 4 / 8) and -w 16-byte literal on 100 GiB.
+
+A step = one pass of the hot path over the resident shard: filter+verify kernel, the one-CTA finish kernel (count +
+sorted list, one synchronisation), policy replay into krep's match_result_t (N>1: + export, gather, key merge; rank 0
+does its host work for step i while step i+1 scans).  Inputs are >= 2.5 GiB >> 126 MB L2, so nothing survives in L2
+between steps.  One JSON line on stdout (rank 0).
 """
 import argparse
 import ctypes as C
@@ -36,6 +42,15 @@ WORKLOADS = {
                    desc="-w 16-byte literal, low hit rate (BASELINE configs[4])"),
     "multi1000": dict(needle=b"kqzvxjwpy", opts={}, flags=0, period=1 << 22, multi=1000,
                       desc="1000 patterns of 6-12 bytes (-f), Aho-Corasick result set (BASELINE configs[3])"),
+    # hit-density workloads (not BASELINE configs): config 1's pattern `the`, planted once per 1 KiB / 64 B
+    "the_1k": dict(needle=b"the", opts={}, flags=0, period=1 << 10,
+                   desc="3-byte literal `the`, one planted per 1 KiB (plus accidental hits), count + all offsets"),
+    "the_64": dict(needle=b"the", opts={}, flags=0, period=1 << 6,
+                   desc="3-byte literal `the`, one planted per 64 B (plus accidental hits), count + all offsets"),
+    "the_1k_c": dict(needle=b"the", opts=dict(count=True), flags=0, period=1 << 10,
+                     desc="`-c the` (count matching lines), one planted per 1 KiB"),
+    "the_64_c": dict(needle=b"the", opts=dict(count=True), flags=0, period=1 << 6,
+                     desc="`-c the` (count matching lines), one planted per 64 B"),
     # side workloads (not BASELINE configs): other regimes of the multi-pattern filter
     "multi1000_8to14": dict(needle=b"kqzvxjwpy", opts={}, flags=0, period=1 << 22, multi=1000, lens=(8, 14),
                             desc="1000 patterns of 8-14 bytes (-f): shortest pattern >= 7, full-word hash filter"),
@@ -43,6 +58,10 @@ WORKLOADS = {
                         desc="1000 patterns of 6-12 bytes, -i"),
 }
 SEED, PLANT_SEED = 0x5EED0001, 0x5EED0002
+# BASELINE configs[2..4]: (workload, TOTAL GiB over all GPUs) — strong scaling over the N the run is launched with
+SIDE_WORKLOADS = [("icase4", 50.0), ("multi1000", 20.0), ("word16", 100.0)]
+# at N = 1 only: hit-density sweep on 10 GiB
+DENSITY_WORKLOADS = [("the_1k", 10.0), ("the_64", 10.0), ("the_1k_c", 10.0), ("the_64_c", 10.0)]
 
 
 def peaks():
@@ -147,33 +166,51 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the stock krep CLI built from /root/reference (oracle/_ref/krep), all host threads
+# reference arm / cpu baseline: the stock krep CLI built from /root/reference (oracle/_ref/krep), all host threads,
+# plus an in-process call of the reference's own kernel function (oracle/_ref/libkrep_ref.so) on one thread.
+# This leg never maps libkrep_b200.so: the corpus sample is written by a child process.
 # ------------------------------------------------------------------------------------------------
-def write_sample(spec_factory, nbytes, path):
-    """Writes corpus bytes [0, nbytes) to `path` using the GPU generator when available, else the host twin."""
-    from krep_b200 import lib
-    try:
-        import torch
-        if torch.cuda.is_available():
-            L = lib.load()
-            t = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
-            torch.cuda.synchronize()
-            L.krep_b200_corpus_generate(C.byref(spec_factory()), t.data_ptr(), 0, nbytes, None)
-            lib.check(L)
-            t[:nbytes].cpu().numpy().tofile(path)
-            del t
-            torch.cuda.empty_cache()
-            return
-    except Exception as e:  # noqa: BLE001
-        print(f"[bench] GPU corpus generation unavailable ({e}); using the host twin", file=sys.stderr)
+_SAMPLE_WRITER = r"""
+import ctypes as C, sys
+sys.path.insert(0, sys.argv[1])
+from krep_b200 import lib
+seed, plant_seed, period, flags, nbytes = (int(x) for x in sys.argv[4:9])
+needle, path = bytes.fromhex(sys.argv[2]), sys.argv[3]
+spec = lib.make_spec(seed, plant_seed, period, needle, flags)
+done = False
+try:
+    import torch
+    if torch.cuda.is_available():
+        L = lib.load()
+        t = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        assert L.krep_b200_corpus_generate(C.byref(spec), t.data_ptr(), 0, nbytes, None) == 0
+        t[:nbytes].cpu().numpy().tofile(path)
+        done = True
+except Exception as e:
+    print(f"[bench] GPU corpus generation unavailable ({e}); using the host twin", file=sys.stderr)
+if not done:
     with open(path, "wb") as f:
         step = 64 << 20
         for off in range(0, nbytes, step):
-            f.write(lib.corpus_host(spec_factory(), off, min(step, nbytes - off)))
+            f.write(lib.corpus_host(spec, off, min(step, nbytes - off)))
+"""
+
+
+def write_sample(wl, nbytes, path):
+    """Writes corpus bytes [0, nbytes) of the workload to `path` in a CHILD process (GPU generator when available, else
+    the host twin), so that the process timing the reference never loads the product library."""
+    r = subprocess.run([sys.executable, "-c", _SAMPLE_WRITER, ROOT, wl["needle"].hex(), path, str(SEED), str(PLANT_SEED),
+                        str(wl["period"]), str(wl["flags"]), str(nbytes)], stdout=sys.stderr, stderr=sys.stderr)
+    if r.returncode != 0 or not os.path.exists(path) or os.path.getsize(path) != nbytes:
+        raise RuntimeError("writing the corpus sample failed")
 
 
 def krep_cli_cmd(cli, wl, sample_path, pat_file):
-    cmd = [cli, "-c", "-o"]                      # -co: count matches (scan + count, no output formatting)
+    if wl["opts"].get("count"):
+        cmd = [cli, "-c"]                        # -c: count matching lines
+    else:
+        cmd = [cli, "-c", "-o"]                  # -co: count matches (scan + count, no output formatting)
     if not wl["opts"].get("case_sensitive", True):
         cmd.append("-i")
     if wl["opts"].get("whole_word"):
@@ -185,26 +222,56 @@ def krep_cli_cmd(cli, wl, sample_path, pat_file):
     return cmd
 
 
-def run_cpu_reference(wl_name, wl, sample_bytes, steps, warmup, keep_file=False):
+def in_process_reference(wl, pats, sample_path, nbytes):
+    """The reference's own kernel function called in-process on the in-memory slice (one call on the whole buffer = the
+    -t 1 result; excludes process start and mmap population).  -> dict or None."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_util as ou
+        from krep_b200.abi import Params          # ctypes struct mirrors only: does not load any library
+        ref = ou.reference()
+        if ref is None:
+            return None
+        with open(sample_path, "rb") as f:
+            data = f.read(nbytes)
+        opts = dict(wl["opts"])
+        if pats:
+            func = "aho_corasick"
+        elif not opts.get("case_sensitive", True) or len(wl["needle"]) > 16:
+            func = "boyer_moore"                  # what simd_avx2_search falls back to (krep.c:4883)
+        elif len(wl["needle"]) < 4:
+            func = "avx2" if opts.get("case_sensitive", True) else "memchr_short"
+        else:
+            func = "sse42"
+        best, cnt = None, 0
+        for _ in range(2):
+            p = Params(pats if pats else wl["needle"], only_matching=not opts.get("count"), **{**opts, "count": True})
+            t0 = time.perf_counter()
+            cnt, _ = ref.run(func, p, data, with_result=False)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return {"value": len(data) / best / 1e9, "unit": "GB/s", "threads": 1, "function": ou.FUNCS[func][1],
+                "sample": f"{len(data) >> 20} MiB in memory, best of 2 calls of the reference's own function "
+                          f"(oracle/_ref/libkrep_ref.so)", "count": cnt}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)}
+
+
+def run_cpu_reference(wl_name, wl, sample_bytes, steps, warmup, in_process=True):
     """Times the unmodified reference on a bounded sample of the workload. -> dict(value GB/s, cores, kind, sample, count, ms)"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import build_oracle
-    from krep_b200 import lib
     _, cli = build_oracle.build_ref()
     shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     sample_path = os.path.join(shm, f"krep_b200_sample_{os.getpid()}.txt")
     pat_file = sample_path + ".pats"
     pats = multi_patterns(wl["multi"], wl["needle"], wl.get("lens", (6, 12))) if wl.get("multi") else None
-
-    def spec_factory():
-        return lib.make_spec(SEED, PLANT_SEED, wl["period"], wl["needle"], wl["flags"])
-
-    write_sample(spec_factory, sample_bytes, sample_path)
+    write_sample(wl, sample_bytes, sample_path)
     if pats:
         with open(pat_file, "wb") as f:
             f.write(b"\n".join(pats) + b"\n")
     cores = os.cpu_count() or 1
-    times, count, single = [], None, None
+    times, count, single, inproc = [], None, None, None
     try:
         if cli:
             cmd = krep_cli_cmd(cli, wl, sample_path, pat_file)
@@ -225,7 +292,7 @@ def run_cpu_reference(wl_name, wl, sample_bytes, steps, warmup, keep_file=False)
                 count = int(last.rsplit(":", 1)[-1])
             kind = "reference"
             how = f"stock krep CLI (oracle/_ref/krep, -msse4.2 -mavx2 build) `{' '.join(cmd[1:-1])} FILE`, default threads"
-            # SURVEY §8d also asks for the -t 1 figure: one run on the first 256 MiB of the same file (head -c via a slice file)
+            # SURVEY §8d also asks for the -t 1 figure: one run on the first 256 MiB of the same file
             try:
                 small = min(sample_bytes, 256 << 20)
                 small_path = sample_path + ".t1"
@@ -239,6 +306,8 @@ def run_cpu_reference(wl_name, wl, sample_bytes, steps, warmup, keep_file=False)
                 os.unlink(small_path)
             except Exception:  # noqa: BLE001
                 single = None
+            if in_process:
+                inproc = in_process_reference(wl, pats, sample_path, min(sample_bytes, 256 << 20))
         else:
             # compiled reference absent: time the scalar oracle port on one core
             sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -255,28 +324,33 @@ def run_cpu_reference(wl_name, wl, sample_bytes, steps, warmup, keep_file=False)
                     times.append(dt)
             kind, cores = "port", 1
             how = "oracle/krep_oracle.c scalar port, 1 thread"
+        if not times:  # every recorded slot was consumed by the shrink step (steps == 1, warmup == 0)
+            t0 = time.perf_counter()
+            subprocess.run(cmd, capture_output=True, text=True)
+            times.append(time.perf_counter() - t0)
     finally:
-        if not keep_file:
-            for pth in (sample_path, pat_file):
-                if os.path.exists(pth):
-                    os.unlink(pth)
-    if not times:  # every recorded slot was consumed by the shrink step (steps == 1, warmup == 0)
-        t0 = time.perf_counter()
-        subprocess.run(cmd, capture_output=True, text=True)
-        times.append(time.perf_counter() - t0)
+        for pth in (sample_path, pat_file):
+            if os.path.exists(pth):
+                os.unlink(pth)
     mean = sum(times) / len(times)
     extra = {}
     if cli and single:
         extra["single_thread"] = single
+    if inproc:
+        extra["in_process"] = inproc
     try:
         with open("/proc/cpuinfo") as f:
             extra["cpu_model"] = next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), None)
     except OSError:
         pass
     return dict(extra, value=sample_bytes / mean / 1e9, best=sample_bytes / min(times) / 1e9, unit="GB/s", cores=cores, kind=kind,
+                sample_bytes=sample_bytes,
                 sample=f"{sample_bytes / GIB:.2f} GiB slice [0, n) of the same corpus in {shm}; whole-process wall, "
                        f"mean of {len(times)} runs after {warmup} warm-up; {how}",
                 count=count, ms=mean * 1e3)
+
+
+CPU_KEYS = ("value", "unit", "cores", "kind", "sample", "sample_bytes", "single_thread", "in_process", "cpu_model")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -292,234 +366,369 @@ def main():
         real_stdout.flush()
 
 
+def workload_config(wl, gib_per_gpu, world, total_gib=None):
+    size = (f"{total_gib:g} GiB synthetic ASCII in total, {gib_per_gpu:g} GiB per GPU" if total_gib is not None
+            else f"{gib_per_gpu:g} GiB synthetic ASCII per GPU")
+    return {"workload": f"{wl['desc']}; {size}, seed {SEED:#x}, 1 planted needle per "
+                        f"{wl['period'] >> 10 if wl['period'] >= 1024 else wl['period'] / 1024:g} KiB",
+            "needle": wl["needle"].decode(), "bytes_per_gpu": int(gib_per_gpu * GIB), "l2": "inputs >> L2 (no flush needed)"}
+
+
+class Runner:
+    """Everything one rank needs to run workloads on its resident shard."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from krep_b200 import lib, sharding
+        self.torch, self.dist, self.lib, self.sharding = torch, dist, lib, sharding
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.cpu_group = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.cpu_group = dist.new_group(backend="gloo")   # host-side barrier: no kernel spinning on an idle GPU
+        self.L = lib.load()
+        assert self.L.krep_b200_init(self.local_rank) == 0, self.L.krep_b200_last_error_string()
+        self.stream = torch.cuda.current_stream()
+        self.sptr = C.c_void_p(self.stream.cuda_stream)
+        self.text = None
+        self.gatherer = sharding.KeyGatherer(self.world, self.rank, "cuda") if self.world > 1 else None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def ensure_text(self, nbytes):
+        if self.text is None or self.text.numel() < nbytes:
+            self.text = None
+            self.torch.cuda.empty_cache()
+            self.text = self.torch.empty(nbytes, dtype=self.torch.uint8, device="cuda")
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x), [float(x)]
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device="cuda")
+        allv = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(allv, t)
+        vals = [float(v.item()) for v in allv]
+        return max(vals), vals
+
+    # -------------------------------------------------------------------------------------------
+    def run(self, name, total_bytes, steps, warmup, sampler=None):
+        """One workload on a corpus of total_bytes sharded over all ranks. -> dict (rank 0) / None."""
+        torch, dist, lib, L = self.torch, self.dist, self.lib, self.L
+        from krep_b200.abi import ALGO_AC, ALGO_AVX2, DeviceResult, Params, Shard
+        wl = WORKLOADS[name]
+        world, rank = self.world, self.rank
+        pats = multi_patterns(wl["multi"], wl["needle"], wl.get("lens", (6, 12))) if wl.get("multi") else None
+        maxlen = max(map(len, pats)) if pats else len(wl["needle"])
+        halo = maxlen + 1
+        g0, own, avail = self.sharding.shard_bounds(total_bytes, world, rank, halo)
+        spec = lib.make_spec(SEED, PLANT_SEED, wl["period"], wl["needle"], wl["flags"])
+        self.ensure_text(avail + 64)
+        assert L.krep_b200_corpus_generate(C.byref(spec), self.text.data_ptr(), g0, avail, self.sptr) == 0
+        prev_byte = lib.corpus_host(spec, g0 - 1, 1)[0] if g0 > 0 else -1
+        next_byte = lib.corpus_host(spec, g0 + avail, 1)[0] if g0 + avail < total_bytes else -1
+        torch.cuda.synchronize()
+        # default mode (positions tracked) unless the workload is a -c count; what select_search_algorithm picks
+        # (krep.c:1771): AVX2 entry -> SSE4.2 kernel for <= 16 bytes, BMH for -i
+        params = Params(pats if pats else wl["needle"], **wl["opts"])
+        if pats:
+            params.struct.ac_trie = 1
+        algo = ALGO_AC if pats else ALGO_AVX2
+        plan = L.krep_b200_plan_create(params.ref(), algo)
+        lib.check(L)
+        shard = Shard(self.text.data_ptr(), avail, 0, own, g0, prev_byte, next_byte)
+        dev = DeviceResult()
+        res = L.krep_b200_match_result_init(1 << 16)
+        count_only = bool(wl["opts"].get("count"))
+        g = self.gatherer
+        state = {"total": 0, "host_ms": 0.0}
+
+        def finish_single():
+            res.contents.count = 0
+            return L.krep_b200_collect(plan, params.ref(), C.byref(dev), res)
+
+        def process(slot):
+            """rank 0, N>1: merge the gathered rows by key and replay them into match_result_t."""
+            t0 = time.perf_counter()
+            keys, counts = g.fetch(slot)
+            res.contents.count = 0
+            arr = C.cast(keys.data_ptr(), C.POINTER(C.c_uint64))
+            state["total"] = L.krep_b200_replay(algo, params.ref(), False, arr, keys.numel(), None, total_bytes, res)
+            state["host_ms"] += (time.perf_counter() - t0) * 1e3
+
+        def scan(ticket_box):
+            rc = L.krep_b200_scan_shard_begin(plan, C.byref(shard), 1, self.sptr, C.byref(ticket_box))
+            assert rc == 0, L.krep_b200_last_error_string()
+
+        def end(ticket_box):
+            rc = L.krep_b200_scan_shard_end(ticket_box.value, C.byref(dev))
+            assert rc == 0, L.krep_b200_last_error_string()
+            return L.krep_b200_last_kernel_ms()
+
+        ticket = C.c_int(0)
+        # warm-up (N>1: also sizes the exchange buffers on all ranks, collectively)
+        for _ in range(max(warmup, 3)):
+            scan(ticket)
+            end(ticket)
+            if world == 1:
+                state["total"] = finish_single()
+            else:
+                while not g.negotiate(int(dev.stored)):
+                    pass
+                L.krep_b200_export_packed(C.byref(dev), g.row_ptr(), g.cap, self.sptr)
+                g.post(0)
+                if rank == 0:
+                    process(0)
+        L.krep_b200_reset_launch_count()
+        state["host_ms"] = 0.0
+        if sampler is not None and rank == 0:
+            sampler.wait_first_sample()
+        self.barrier()
+        if sampler is not None:
+            sampler.mark_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        xa = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        xb = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        kernel_ms = []
+        e0.record(self.stream)
+        for i in range(steps):
+            scan(ticket)                                   # enqueue scan i
+            if world > 1 and rank == 0 and i > 0:
+                process((i - 1) & 1)                       # host work of step i-1 while scan i runs
+            kernel_ms.append(end(ticket))                  # the step's one synchronisation
+            if world == 1:
+                state["total"] = finish_single()
+            else:
+                xa[i].record(self.stream)
+                L.krep_b200_export_packed(C.byref(dev), g.row_ptr(), g.cap, self.sptr)
+                g.post(i & 1)
+                xb[i].record(self.stream)
+        if world > 1 and rank == 0 and steps:
+            process((steps - 1) & 1)
+        e1.record(self.stream)
+        self.barrier()
+        if sampler is not None:
+            sampler.mark_end()
+        elapsed_ms = e0.elapsed_time(e1)
+        launches = int(L.krep_b200_launch_count())
+        exch = sum(a.elapsed_time(b) for a, b in zip(xa, xb)) / max(steps, 1) if world > 1 else 0.0
+        step_max, step_all = self.max_over_ranks(elapsed_ms / max(steps, 1))
+        k_max, k_all = self.max_over_ranks(sum(kernel_ms) / max(len(kernel_ms), 1))
+        x_max, x_all = self.max_over_ranks(exch)
+        if world > 1:
+            flag = torch.tensor([1 if (rank == 0 and g.overflowed) else 0], dtype=torch.int64, device="cuda")
+            dist.all_reduce(flag)
+            assert int(flag.item()) == 0, "key exchange overflowed its buffers in the timed loop"
+        out = None
+        if rank == 0:
+            peak, peak_src = peaks()
+            per_gpu = total_bytes / world
+            achieved = per_gpu / (k_max * 1e-3) / 1e9
+            first = [(res.contents.positions[i].start_offset, res.contents.positions[i].end_offset)
+                     for i in range(min(3, res.contents.count))]
+            out = {
+                "value": total_bytes / (step_max * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": step_max, "steps": steps,
+                "total_bytes": total_bytes, "bytes_per_gpu": int(per_gpu), "matches": int(state["total"]), "first_matches": first,
+                "filter": L.krep_b200_plan_filter_name(plan).decode(), "halo": halo,
+                "kernel_ms": k_max, "kernel_ms_per_rank": k_all, "ms_per_step_per_rank": step_all,
+                "exchange_ms": x_max, "exchange_ms_per_rank": x_all, "rank0_host_ms_per_step": state["host_ms"] / max(steps, 1),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "kernel_ms": k_max, "algorithmic_bytes_per_launch": int(per_gpu), "peak_source": peak_src,
+                             "traffic": measured_traffic(name, per_gpu)},
+                "gpu_launches": launches,
+            }
+        self._last = dict(plan=plan, params=params, res=res, pats=pats, algo=algo, total=int(state["total"]),
+                          own=own, avail=avail, g0=g0, spec=spec, halo=halo)
+        return out
+
+    def release_last(self):
+        last = getattr(self, "_last", None)
+        if last:
+            last["params"].struct.ac_trie = None
+            self.L.krep_b200_plan_destroy(last["plan"])
+            self.L.krep_b200_match_result_free(last["res"])
+            self._last = None
+
+    # -------------------------------------------------------------------------------------------
+    def e2e(self, name, total_bytes, steps):
+        """The same metric through the search_func_t entry point on PINNED HOST text, copies inside the timed region.
+        N = 1: this process, its GPU.  N > 1: ONE call in ONE process (rank 0) that spreads the text over all N GPUs
+        (krep_b200_set_devices) — what a krep host calling the drop-in gets; the other ranks wait on a host barrier."""
+        torch, lib, L = self.torch, self.lib, self.L
+        last = self._last
+        wl = WORKLOADS[name]
+        world, rank = self.world, self.rank
+        out = None
+        if rank == 0:
+            t_alloc = time.perf_counter()
+            host = torch.empty(total_bytes, dtype=torch.uint8, pin_memory=True)
+            t_alloc = time.perf_counter() - t_alloc
+            piece = min(self.text.numel() - 64, total_bytes) // 16 * 16
+            for off in range(0, total_bytes, piece):     # materialise the whole corpus in host memory through GPU 0
+                ln = min(piece, total_bytes - off)
+                assert L.krep_b200_corpus_generate(C.byref(last["spec"]), self.text.data_ptr(), off, ln, self.sptr) == 0
+                host[off:off + ln].copy_(self.text[:ln])
+            torch.cuda.synchronize()
+            entry = "aho_corasick" if last["pats"] else "avx2"
+            fn = getattr(L, lib.SEARCH_ENTRIES[entry])
+            params, res = last["params"], last["res"]
+            L.krep_b200_set_only_matching(False)
+            devs = (C.c_int * world)(*range(world))
+            L.krep_b200_set_devices(devs, world)
+
+            def e2e_step():
+                res.contents.count = 0
+                c = fn(params.ref(), C.c_void_p(host.data_ptr()), total_bytes, res)
+                lib.check(L)
+                return int(c)
+
+            e2e_step()                                     # warm-up: contexts on every device, rings, plan uploads
+            t0 = time.perf_counter()
+            got = 0
+            for _ in range(steps):
+                got = e2e_step()
+            dt = (time.perf_counter() - t0) / steps
+            L.krep_b200_set_devices(None, 0)
+            out = {"value": total_bytes / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": total_bytes,
+                   "d2h_bytes_per_step": 8 * world + 8 * got, "ms_per_step": dt * 1e3, "steps": steps,
+                   "api": lib.SEARCH_ENTRIES[entry] + "(params, pinned host text, len, match_result_t*) — one call, one process, "
+                          f"{world} device(s) (krep_b200_set_devices)",
+                   "bytes": total_bytes, "matches": got, "agrees_with_device_path": got == last["total"],
+                   "scan_kernel_ms_slowest_device": float(L.krep_b200_last_kernel_ms()), "pinned_alloc_s": t_alloc}
+            del host
+        if world > 1:
+            self.dist.barrier(group=self.cpu_group)
+        return out
+
+
+def measured_traffic(name, per_gpu_bytes):
+    """DRAM bytes per launch from the committed ncu --set full capture of this workload's kernel (profiles/), scaled to
+    this run's shard size; None when no capture of the current kernels is on file."""
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        tr = json.load(open(tpath)).get(name)
+        if tr:
+            return tr["dram_bytes_per_launch"] * (per_gpu_bytes / tr["corpus_bytes"])
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def _main(out_stream):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gib", type=float, default=10.0, help="corpus GiB per GPU")
+    ap.add_argument("--gib", type=float, default=10.0, help="headline corpus GiB per GPU")
     ap.add_argument("--workload", default="literal8", choices=list(WORKLOADS))
     ap.add_argument("--cpu-sample-gib", type=float, default=2.0)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--side-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the BASELINE configs[2..4] side workloads")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
     metric = "GB/s scanned (HBM-resident corpus)"
-    config = {"workload": f"{wl['desc']}; {args.gib:g} GiB synthetic ASCII per GPU, seed {SEED:#x}, "
-                          f"1 planted needle per {wl['period'] >> 10} KiB",
-              "needle": wl["needle"].decode(), "bytes_per_gpu": int(args.gib * GIB), "l2": "inputs >> L2 (no flush needed)"}
+    config = workload_config(wl, args.gib, world)
 
     if args.impl == "reference":
         if rank != 0:
             return
         sample = int(min(args.cpu_sample_gib, args.gib) * GIB)
         r = run_cpu_reference(args.workload, wl, sample, max(args.steps, 1), args.warmup)
+        config["cpu_slice_bytes"] = r["sample_bytes"]
         print(json.dumps({
             "impl": "reference", "metric": metric, "value": r["value"], "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "single_thread", "cpu_model") if k in r},
+            "cpu_baseline": {k: r[k] for k in CPU_KEYS if k in r},
             "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "matches_in_sample": r["count"],
         }), file=out_stream)
         return
 
-    import torch
-    import torch.distributed as dist
-    from krep_b200 import lib, sharding
-    from krep_b200.abi import ALGO_AC, ALGO_AVX2, DeviceResult, Params, Shard
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    L = lib.load()
-    assert L.krep_b200_init(local_rank) == 0, L.krep_b200_last_error_string()
-
+    R = Runner(args)
+    torch, dist = R.torch, R.dist
     n = int(args.gib * GIB)
     n -= n % 16
-    pats = multi_patterns(wl["multi"], wl["needle"], wl.get("lens", (6, 12))) if wl.get("multi") else None
-    maxlen = max(map(len, pats)) if pats else len(wl["needle"])
-    halo = maxlen + 1
-    last = rank == world - 1
-    g0, own_len, avail = sharding.shard_bounds(world * n, world, rank, halo)   # weak scaling: n owned bytes per GPU
-    assert own_len == n
-    spec = lib.make_spec(SEED, PLANT_SEED, wl["period"], wl["needle"], wl["flags"])
-    text = torch.empty(avail + 64, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream()
-    sptr = C.c_void_p(stream.cuda_stream)
-    assert L.krep_b200_corpus_generate(C.byref(spec), text.data_ptr(), g0, avail, sptr) == 0
-    prev_byte = -1
-    if rank > 0:
-        prev_byte = lib.corpus_host(spec, g0 - 1, 1)[0]
-    next_byte = -1 if last else lib.corpus_host(spec, g0 + avail, 1)[0]
-    torch.cuda.synchronize()
-
-    # -co semantics would not need offsets; the workload asks for count + all offsets -> default mode (track positions)
-    params = Params(pats if pats else wl["needle"], **wl["opts"])
-    algo = ALGO_AC if pats else ALGO_AVX2      # what select_search_algorithm picks (krep.c:1771): AVX2 entry -> SSE4.2 kernel
-    plan = L.krep_b200_plan_create(params.ref(), algo)
-    lib.check(L)
-    shard = Shard(text.data_ptr(), avail, 0, n, g0, prev_byte, next_byte)
-    dev = DeviceResult()
-    res = L.krep_b200_match_result_init(1 << 16)
-
-    gatherer = sharding.KeyGatherer(world, rank, "cuda") if world > 1 else None
-    checked = [True]   # warm-up steps size the exchange buffers on all ranks; the timed steps then run unchecked
-
-    def step():
-        rc = L.krep_b200_scan_shard(plan, C.byref(shard), 1, sptr, C.byref(dev))
-        assert rc == 0, L.krep_b200_last_error_string()
-        kms = L.krep_b200_last_kernel_ms()
-        if world == 1:
-            res.contents.count = 0
-            total = L.krep_b200_collect(plan, params.ref(), C.byref(dev), res)
-            return total, kms
-        # N>1: ONE collective — every rank all_gathers [count, sorted keys]; rank 0 reads the rows back and replays the
-        # concatenation (rank order = global order), krep_b200/sharding.py
-        while True:
-            n_mine = int(dev.stored)
-            if n_mine <= gatherer.cap:
-                L.krep_b200_export_keys(C.byref(dev), gatherer.key_buffer().data_ptr(), n_mine, sptr)
-            keys, counts, retry = gatherer.exchange(n_mine, check=checked[0])
-            if not retry:
-                break
-        total = 0
-        if rank == 0:
-            res.contents.count = 0
-            arr = C.cast(keys.data_ptr(), C.POINTER(C.c_uint64))
-            total = L.krep_b200_replay(algo, params.ref(), False, arr, keys.numel(), None, world * n, res)
-        return total, kms
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(R.local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3) if args.steps else 0):
-        step()
-    L.krep_b200_reset_launch_count()
-    checked[0] = False
-    if rank == 0:
-        sampler.wait_first_sample()
-    barrier()
-    sampler.mark_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    e0.record(stream)
-    total = 0
-    for _ in range(args.steps):
-        total, kms = step()
-        kernel_ms.append(kms)
-    e1.record(stream)
-    barrier()
-    sampler.mark_end()
+    head = R.run(args.workload, world * n, args.steps, args.warmup, sampler)     # weak scaling: n owned bytes per GPU
     clocks = sampler.stop() if rank == 0 else None
-    elapsed_ms = e0.elapsed_time(e1)
-    launches = int(L.krep_b200_launch_count())
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-        km = torch.tensor([sum(kernel_ms) / len(kernel_ms)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(km, op=dist.ReduceOp.MAX)
-        kernel_avg_ms = float(km.item())
-    else:
-        kernel_avg_ms = sum(kernel_ms) / len(kernel_ms)
-    ms_per_step = elapsed_ms / args.steps
-    value = world * n / (ms_per_step * 1e-3) / 1e9
-    match_count = int(total)
-    first = [(res.contents.positions[i].start_offset, res.contents.positions[i].end_offset)
-             for i in range(min(3, res.contents.count))] if rank == 0 else []
-
-    # ---- e2e: same metric through the search_func_t entry point with HOST buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        host = torch.empty(avail, dtype=torch.uint8, pin_memory=True)
-        host.copy_(text[:avail])
-        torch.cuda.synchronize()
-        entry = "aho_corasick" if pats else "avx2"
-        fn = getattr(L, lib.SEARCH_ENTRIES[entry])
-        if pats:
-            params.struct.ac_trie = L.krep_b200_ac_trie_build(params.ref())
-        L.krep_b200_set_only_matching(False)
+        e2e = R.e2e(args.workload, world * n, args.e2e_steps)
+    R.release_last()
 
-        def e2e_step():
-            res.contents.count = 0
-            c = fn(params.ref(), C.c_void_p(host.data_ptr()), avail, res)
-            lib.check(L)
-            # ownership by start offset: matches that start in the halo belong to the next rank
-            own = sum(1 for i in range(res.contents.count) if res.contents.positions[i].start_offset < n) \
-                if not last else int(c)
-            return own
-
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        own = 0
-        for _ in range(args.e2e_steps):
-            own = e2e_step()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-            c = torch.tensor([own], dtype=torch.int64, device="cuda")
-            dist.all_reduce(c)
-            own = int(c.item())
-        e2e = {"value": world * n / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": world * avail,
-               "d2h_bytes_per_step": 8 * world + 8 * own, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
-               "api": lib.SEARCH_ENTRIES[entry] + "(params, pinned host text, len, match_result_t*)",
-               "matches": own, "agrees_with_device_path": own == match_count}
-        params.struct.ac_trie = None
-        del host
+    side = {}
+    if not args.no_side and args.workload == "literal8":
+        todo = list(SIDE_WORKLOADS) + (list(DENSITY_WORKLOADS) if world == 1 else [])
+        for name, total_gib in todo:
+            total = int(total_gib * GIB) // (16 * world) * (16 * world)
+            try:
+                r = R.run(name, total, args.side_steps, 3)
+            except Exception as e:  # noqa: BLE001  (all ranks fail alike: sizes and code are identical)
+                r = {"error": str(e)} if rank == 0 else None
+            R.release_last()
+            if rank == 0 and r is not None:
+                r["config"] = workload_config(WORKLOADS[name], total_gib / world, world, total_gib)
+                r["scaling"] = "strong" if (name, total_gib) in SIDE_WORKLOADS else "n/a (N = 1 only)"
+                side[name] = r
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    R.text = None
+    torch.cuda.empty_cache()
 
-    peak, peak_src = peaks()
-    achieved = n / (kernel_avg_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tr = json.load(open(tpath)).get(args.workload)
-            if tr:
-                traffic = tr["dram_bytes_per_launch"] * (n / tr["corpus_bytes"])
-        except Exception:  # noqa: BLE001
-            pass
     out = {
-        "metric": metric, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic", "config": dict(config, filter=L.krep_b200_plan_filter_name(plan).decode(),
-                                            parallelism=f"{world} shard(s), owned by match start, halo {halo} B"),
-        "matches": match_count, "first_matches": first,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_avg_ms,
-                     "algorithmic_bytes_per_launch": n,
-                     "note": "achieved = corpus bytes of one shard / mean scan-kernel duration (CUDA events on the launching stream, inside the timed region; max over ranks)"},
-        "gpu_launches": launches, "clocks": clocks,
+        "metric": metric, "value": head["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": dict(config, filter=head["filter"],
+                                            parallelism=f"{world} shard(s), owned by match start, halo {head['halo']} B"),
+        "matches": head["matches"], "first_matches": head["first_matches"],
+        "roofline": dict(head["roofline"], note="achieved = corpus bytes of one shard / mean scan-kernel duration (CUDA events on the "
+                                               "launching stream, inside the timed region; max over ranks)"),
+        "kernel_ms_per_rank": head["kernel_ms_per_rank"], "ms_per_step_per_rank": head["ms_per_step_per_rank"],
+        "exchange_ms": head["exchange_ms"], "exchange_ms_per_rank": head["exchange_ms_per_rank"],
+        "rank0_host_ms_per_step": head["rank0_host_ms_per_step"],
+        "gpu_launches": head["gpu_launches"], "clocks": clocks,
     }
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu and world == 1:
         try:
             r = run_cpu_reference(args.workload, wl, int(min(args.cpu_sample_gib, args.gib) * GIB), 3, 1)
-            out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "single_thread", "cpu_model") if k in r}
+            out["cpu_baseline"] = {k: r[k] for k in CPU_KEYS if k in r}
             out["cpu_baseline"]["matches_in_sample"] = r["count"]
+            out["config"]["cpu_slice_bytes"] = r["sample_bytes"]
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"error": str(e)}
+        for name, r in side.items():
+            if "error" in r:
+                continue
+            try:
+                c = run_cpu_reference(name, WORKLOADS[name], 1 << 30, 2, 1)
+                r["cpu_baseline"] = {k: c[k] for k in CPU_KEYS if k in c}
+                r["cpu_baseline"]["matches_in_sample"] = c["count"]
+            except Exception as e:  # noqa: BLE001
+                r["cpu_baseline"] = {"error": str(e)}
+    if side:
+        out["workloads"] = side
     print(json.dumps(out), file=out_stream)
     if world > 1:
         dist.destroy_process_group()

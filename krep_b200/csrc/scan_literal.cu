@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ 
     const uint4 *__restrict__ t4 = reinterpret_cast<const uint4 *>(p.text);
     const uint32_t fold = p.fold, mask = p.win_mask, k0 = p.K[0];
     const uint32_t c1 = p.mulc[0], c2 = p.mulc[1], c3 = p.mulc[2]; // 2^24, 2^16, 2^8
+    const bool lane31 = (threadIdx.x & 31) == 31;
     unsigned long long local_cnt = 0;
     const uint64_t tile = (uint64_t)blockDim.x * UNROLL;
     const uint64_t stride = (uint64_t)gridDim.x * tile;
@@ -233,7 +234,15 @@ __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ 
         {
             const uint4 *q = t4 + g0 + (uint64_t)u * blockDim.x + threadIdx.x;
             v[u] = WLOAD(q);
-            nx[u] = __ldg(reinterpret_cast<const uint32_t *>(q + 1)); // first word of the next vector (L1/L2 hit)
+            // the word after the vector is the next lane's v.x: only lane 31 has to load it (one sector per 512 bytes
+            // instead of one 4-byte request per lane)
+            nx[u] = lane31 ? __ldg(reinterpret_cast<const uint32_t *>(q + 1)) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+        {
+            const uint32_t nb = __shfl_down_sync(0xffffffffu, v[u].x, 1);
+            if (!lane31) nx[u] = nb;
         }
         uint32_t hm = 0; // bit u: vector u holds a candidate
 #pragma unroll

@@ -1,7 +1,7 @@
 #!/bin/bash
 # What a krep user sees: the stock CLI vs the same CLI relinked against libkrep_b200.so, whole-process wall time,
-# on a corpus file in /dev/shm (page cache).  Usage: bash scripts/gpu_cli_timing.sh [GiB]
-G=${1:-8}; O=gpurun_out; mkdir -p $O
+# on a corpus file in /dev/shm (page cache).  Usage: bash scripts/gpu_cli_timing.sh [GiB] [tag]
+G=${1:-8}; TAG=${2:-cli}; O=gpurun_out; mkdir -p $O
 python - <<PY
 import ctypes as C, sys, torch
 sys.path.insert(0, ".")
@@ -16,11 +16,22 @@ t[:n].cpu().numpy().tofile("/dev/shm/krep_cli_corpus.txt")
 open("/dev/shm/krep_cli_pats.txt", "wb").write(b"\n".join(bench.multi_patterns(1000, b"kqzvxjwpy")) + b"\n")
 PY
 F=/dev/shm/krep_cli_corpus.txt; P=/dev/shm/krep_cli_pats.txt
-run() { local s=$(date +%s.%N); "$@" > /tmp/cli_out.txt 2>/tmp/cli_err.txt; local rc=$?; local e=$(date +%s.%N); echo "$(echo "$e - $s" | bc -l 2>/dev/null || python -c "print($e-$s)") s rc=$rc out=$(tail -c 80 /tmp/cli_out.txt | tr '\n' ' ')"; }
-for args in "-c qzXv9Kpw" "-c -o qzXv9Kpw" "-c -i QzXv" "-c -w needleneedle0016" "-c -o -f $P"; do
+run() { python - "$@" <<'PY'
+import subprocess, sys, time
+t0 = time.perf_counter(); r = subprocess.run(sys.argv[1:], capture_output=True); dt = time.perf_counter() - t0
+print(f"{dt:.3f} s rc={r.returncode} out={r.stdout.decode()[-80:].strip()}")
+PY
+}
+{
+echo "# $(nvidia-smi --query-gpu=name --format=csv,noheader | head -1) x $(nvidia-smi -L | wc -l), $(nproc) host threads, corpus $G GiB in /dev/shm"
+build/cuinit_probe 1
+for args in "-c qzXv9Kpw" "-c -o qzXv9Kpw" "-c -i QzXv" "-c -w needleneedle0016" "-c -o -f $P" "-c the"; do
   for bin in oracle/_ref/krep build/krep_gpu/krep; do
     run $bin $args $F > /dev/null   # warm
-    echo "$bin $args : $(run $bin $args $F)"
+    echo "$bin $args : $(run $bin $args $F) | $(run $bin $args $F)"
   done
-done | tee $O/cli_timing.txt
+done
+echo "# phase trace of one GPU-backed run (KREP_B200_TRACE=1)"
+KREP_B200_TRACE=1 build/krep_gpu/krep -c qzXv9Kpw $F 2>&1 | tail -40
+} 2>&1 | tee $O/${TAG}_timing.txt
 rm -f $F $P
