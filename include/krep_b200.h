@@ -260,6 +260,30 @@ float krep_b200_last_kernel_ms(void);
 uint64_t krep_b200_launch_count(void);
 void krep_b200_reset_launch_count(void);
 
+/* Fused -c (count_lines_mode) for single literals: the scan itself counts the lines that hold an occurrence
+ * (krep.c:1331-1351 and the equivalent branches of the other literal kernels), so only this record leaves the GPU.
+ * A shard that cuts lines still gives an exact total: records of shards in text order are folded with
+ * krep_b200_combine_line_counts, which subtracts a line counted on both sides of a cut. */
+typedef struct
+{
+   uint64_t lines;    /* lines of this shard that hold an occurrence it owns                                     */
+   uint32_t flags;    /* KREP_B200_LINES_*                                                                        */
+   uint32_t reserved;
+} krep_b200_line_count_t;
+enum
+{
+   KREP_B200_LINES_HAS_HIT = 1,      /* the shard owns at least one occurrence                                       */
+   KREP_B200_LINES_FIRST_OPEN = 2,   /* its first occurrence lies before its first newline (the line began earlier)  */
+   KREP_B200_LINES_LAST_PENDING = 4, /* no newline between its last occurrence and its end (the line goes on)         */
+   KREP_B200_LINES_HAS_NL = 8        /* the shard holds a newline (computed for shards without an occurrence)         */
+};
+/* Plans created from params with count_lines_mode set; not for pattern sets, needles of 17..64 bytes taken by the
+ * window kernels, patterns containing a newline or -w plans in tag mode (those need krep_b200_scan_shard +
+ * krep_b200_collect): returns a negative error for them. */
+int krep_b200_count_lines_shard(const krep_b200_plan_t *plan, const search_params_t *params, const krep_b200_shard_t *shard,
+                                void *stream, krep_b200_line_count_t *out);
+uint64_t krep_b200_combine_line_counts(const krep_b200_line_count_t *recs, size_t n, size_t max_count);
+
 /* Apply the emulated reference kernel's policy (overlap rule, -w, -c, -m) to a
  * shard result and deliver it as krep's match_result_t (host, malloc memory).
  * Count-lines mode (-c) uses the line bounds the scan computed on the device

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkrep_b200.so")
-SOURCES = ["engine.cu", "scan_literal.cu", "scan_multi.cu", "host_api.cu", "semantics.cpp"]
+SOURCES = ["engine.cu", "scan_literal.cu", "scan_multi.cu", "scan_count.cu", "host_api.cu", "semantics.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-fopenmp,-Wall,-Wno-unused-function", "-Xptxas", "-v"]

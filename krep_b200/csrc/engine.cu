@@ -143,8 +143,6 @@ static int ctx_create(DevCtx &E, int device)
         CK(cudaEventCreate(&E.ev_a[s]));
         CK(cudaEventCreate(&E.ev_b[s]));
     }
-    CK(cudaMalloc(&E.d_line_out, 64));
-    CK(cudaHostAlloc(&E.h_line_out, 64, cudaHostAllocMapped | cudaHostAllocPortable));
     E.ready = true;
     trace("device %d: context ready (%s, %d SMs)", device, prop.name, E.sm_count);
     return 0;

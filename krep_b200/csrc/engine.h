@@ -58,7 +58,8 @@ struct DevCtx
     // fused -c (scan_count.cu): one record per partition
     void *d_line_recs = nullptr;
     uint64_t line_recs_cap = 0;
-    uint64_t *d_line_out = nullptr, *h_line_out = nullptr;
+    uint64_t *d_line_out = nullptr, *h_line_out = nullptr; // shard records (lines, flags), 2 words each; h_ is mapped pinned
+    uint64_t line_out_cap = 0;
     // host-text entry points: device ring the caller's buffer streams through + pinned staging ring + key read-back
     uint8_t *d_ring = nullptr;
     size_t ring_slot_bytes = 0;
@@ -114,6 +115,12 @@ void reset_kernel_ms();
 float get_kernel_ms();
 void set_kernel_ms(float ms);
 void trace(const char *fmt, ...); // KREP_B200_TRACE=1: "[krep_b200 +12.3 ms] ..." on stderr
+
+// scan_count.cu — fused -c (count of matching lines computed in the scan)
+bool count_lines_eligible(const Plan *plan, const search_params_t *P, int algo);
+int ensure_line_out(DevCtx &C, uint64_t n);
+int launch_count_lines(DevCtx &C, const Plan *plan, const krep_b200_shard_t *sh, cudaStream_t stream, uint64_t index);
+uint64_t combine_line_records(const uint64_t *recs, size_t n); // records in text order -> number of matching lines
 
 // Merges ascending key lists into dst (room for the sum of counts); lists of literal keys from rank-ordered shards are
 // already globally ordered, lists of pattern-set keys (ordered by END offset but owned by START offset) are not.

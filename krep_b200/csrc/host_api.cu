@@ -248,6 +248,8 @@ struct RangeJob
     size_t n = 0, begin = 0, end = 0, chunk = 0;
     int want_positions = 0;
     bool pinned = false;
+    bool count_lines = false; // fused -c: every chunk leaves one line record instead of occurrence keys
+    std::vector<uint64_t> line_recs; // (lines, flags) per chunk, text order
     // results
     int rc = 0;
     ScanOut so;
@@ -271,6 +273,7 @@ static int stream_range(RangeJob &J)
     if (ensure_ring(E, std::min(chunk, span) + halo + 64, nslots) != 0) return -2;
     if (!J.pinned && ensure_stage(E, std::min(chunk, span) + halo + 64, nslots) != 0) return -2;
     if (J.want_positions && ensure_keys(E, 1) != 0) return -2;
+    if (J.count_lines && ensure_line_out(E, nchunks) != 0) return -2;
     reset_kernel_ms();
     const int slot = 0;
     for (int attempt = 0; attempt < 3; attempt++)
@@ -306,13 +309,14 @@ static int stream_range(RangeJob &J)
             part.next_byte = off + src_len < n ? (int32_t)(uint8_t)J.text[off + src_len] : -1;
             cudaEvent_t a = pool_event(E, 2 * c), b = pool_event(E, 2 * c + 1);
             CKH(cudaEventRecord(a, E.scan_stream));
-            int rc = launch_scan(E, plan, &part, J.want_positions, E.scan_stream);
+            int rc = J.count_lines ? launch_count_lines(E, plan, &part, E.scan_stream, c)
+                                   : launch_scan(E, plan, &part, J.want_positions, E.scan_stream);
             if (rc != 0) return rc;
             CKH(cudaEventRecord(b, E.scan_stream));
             CKH(cudaEventRecord(E.ring_scanned[rs], E.scan_stream));
         }
         CKH(cudaGetLastError());
-        if (finish_scan(E, slot, J.want_positions, E.scan_stream) != 0) return -2;
+        if (!J.count_lines && finish_scan(E, slot, J.want_positions, E.scan_stream) != 0) return -2;
         CKH(cudaStreamSynchronize(E.scan_stream));
         for (auto &s : E.stage) s.in_flight = false;
         for (size_t c = 0; c < nchunks; c++)
@@ -320,6 +324,12 @@ static int stream_range(RangeJob &J)
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, E.ev_pool[2 * c], E.ev_pool[2 * c + 1]) == cudaSuccess) add_kernel_ms(ms);
             else cudaGetLastError();
+        }
+        if (J.count_lines)
+        {
+            J.line_recs.assign(E.h_line_out, E.h_line_out + 2 * nchunks);
+            J.so = ScanOut();
+            return 0;
         }
         const uint64_t cnt = E.h_pack[slot][0];
         J.so = ScanOut();
@@ -390,7 +400,7 @@ struct HostScan
     std::vector<uint64_t> merged; // backing store when several devices contributed
 };
 
-static int stage_and_scan(const Plan *plan, const char *text, size_t n, int want_positions, HostScan *hs)
+static int stage_and_scan(const Plan *plan, const char *text, size_t n, int want_positions, HostScan *hs, bool count_lines = false)
 {
     const bool pinned = is_pinned(text);
     const size_t chunk = pinned ? env_mb("KREP_B200_CHUNK_MB", 256) : env_mb("KREP_B200_STAGE_MB", 32);
@@ -421,6 +431,7 @@ static int stage_and_scan(const Plan *plan, const char *text, size_t n, int want
         J.end = std::min((i + 1) * per * chunk, n);
         J.want_positions = want_positions;
         J.pinned = pinned;
+        J.count_lines = count_lines;
     }
     trace("search: %zu bytes (%s host memory), %zu device(s), %zu range(s), chunk %zu MiB", n, pinned ? "pinned" : "pageable", D, R,
           chunk >> 20);
@@ -481,9 +492,18 @@ static int stage_and_scan(const Plan *plan, const char *text, size_t n, int want
         set_kernel_ms(*std::max_element(kdev.begin(), kdev.end())); // devices scan concurrently: the slowest one's time
     }
     hs->count = 0;
-    for (auto &J : jobs) hs->count += J.so.count;
     hs->keys = nullptr;
     hs->nkeys = 0;
+    if (count_lines)
+    {
+        // chunk records of all ranges, in text order -> matching lines (a line cut by a chunk / range / device edge is
+        // counted on both sides and subtracted once)
+        std::vector<uint64_t> all;
+        for (auto &J : jobs) all.insert(all.end(), J.line_recs.begin(), J.line_recs.end());
+        hs->count = combine_line_records(all.data(), all.size() / 2);
+        return 0;
+    }
+    for (auto &J : jobs) hs->count += J.so.count;
     if (!want_positions) return 0;
     for (auto &J : jobs)
     {
@@ -640,6 +660,13 @@ static uint64_t run_search(int entry_algo, const search_params_t *P, const char 
     const bool need_list = P->count_lines_mode || want_result || !keeps_all(algo, only_matching, P, plan) ||
                            plan->whole_word == 2;
     HostScan hs;
+    if (count_lines_eligible(plan, P, algo) && !getenv("KREP_B200_NO_FUSED_COUNT"))
+    {
+        // -c: the scan counts matching lines itself; the -m limit caps the count (every kernel stops at max_count lines,
+        // max_count == 0 was answered above)
+        if (stage_and_scan(plan, text, n, 0, &hs, true) != 0) return 0;
+        return std::min<uint64_t>(hs.count, P->max_count);
+    }
     if (stage_and_scan(plan, text, n, need_list ? 1 : 0, &hs) != 0) return 0;
     if (!need_list) return limited_count(algo, P, hs.count);
     Replay r{hs.keys, (size_t)hs.nkeys, text, n, 0};
@@ -992,6 +1019,59 @@ uint64_t krep_b200_replay_lines(int algo, const search_params_t *P, bool only_ma
     algo = resolve_algo(P, algo);
     const uint32_t m = algo == KREP_B200_ALGO_MEMCHR ? 1u : (uint32_t)P->pattern_len;
     return replay_literal(algo, P, only_matching, m, r, result);
+}
+
+// ---- fused -c on resident shards ----
+int krep_b200_count_lines_shard(const krep_b200_plan_t *plan_, const search_params_t *P, const krep_b200_shard_t *shard, void *stream,
+                                krep_b200_line_count_t *out)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    clear_error();
+    const Plan *plan = reinterpret_cast<const Plan *>(plan_);
+    if (!plan || !P || !shard || !out)
+    {
+        set_error(-3, "krep_b200_count_lines_shard: null argument");
+        return -3;
+    }
+    if (!count_lines_eligible(plan, P, plan->algo))
+    {
+        set_error(-3, "krep_b200_count_lines_shard: this plan's -c result needs the occurrence list (pattern set, window kernel, "
+                      "newline in the pattern or tag-mode -w): use krep_b200_scan_shard + krep_b200_collect");
+        return -3;
+    }
+    DeviceGuard guard;
+    cudaPointerAttributes a;
+    DevCtx *C = (cudaPointerGetAttributes(&a, shard->d_text) == cudaSuccess && a.type == cudaMemoryTypeDevice) ? ctx_get(a.device) : ctx_primary();
+    if (!C) return -1;
+    cudaStream_t st = stream ? (cudaStream_t)stream : C->scan_stream;
+    reset_kernel_ms();
+    if (cudaEventRecord(C->ev_a[0], st) != cudaSuccess) return -2;
+    int rc = launch_count_lines(*C, plan, shard, st, 0);
+    if (rc != 0) return rc;
+    if (cudaEventRecord(C->ev_b[0], st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    {
+        set_error(-2, "CUDA error in the fused line count (%s)", cudaGetErrorString(cudaGetLastError()));
+        return -2;
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, C->ev_a[0], C->ev_b[0]);
+    add_kernel_ms(ms);
+    out->lines = C->h_line_out[0];
+    out->flags = (uint32_t)C->h_line_out[1];
+    out->reserved = 0;
+    return 0;
+}
+
+uint64_t krep_b200_combine_line_counts(const krep_b200_line_count_t *recs, size_t n, size_t max_count)
+{
+    if (!recs) return 0;
+    std::vector<uint64_t> flat(2 * n);
+    for (size_t i = 0; i < n; i++)
+    {
+        flat[2 * i] = recs[i].lines;
+        flat[2 * i + 1] = recs[i].flags;
+    }
+    return std::min<uint64_t>(combine_line_records(flat.data(), n), max_count);
 }
 
 // ---- shard result -> match_result_t under the emulated kernel's policy ----

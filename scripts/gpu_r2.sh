@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,memory.total --format=c
 nproc >> $O/${TAG}_gpu.txt; grep -m1 "model name" /proc/cpuinfo >> $O/${TAG}_gpu.txt; free -g | head -2 >> $O/${TAG}_gpu.txt
 for w in $WHAT; do case $w in
 tests)
-  timeout 1800 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest_gpu.log
+  timeout 1800 python -m pytest tests -m gpu -q > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest_gpu.log
   tail -15 $O/${TAG}_pytest_gpu.log
   timeout 300 python __graft_entry__.py smoke > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> $O/${TAG}_smoke.log; tail -2 $O/${TAG}_smoke.log ;;
 bench)
