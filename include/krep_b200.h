@@ -91,6 +91,11 @@ typedef uint64_t (*search_func_t)(const search_params_t *params,
  * count 0 and krep_b200_last_error() != 0. */
 int krep_b200_init(int device);
 int krep_b200_device_count(void);          /* CUDA devices visible to the process */
+/* Non-blocking: starts CUDA initialisation and the primary device's context on a background thread and returns.  A
+ * host calls it as soon as it knows a literal search is coming (krep: after option parsing, before search_file opens
+ * and maps the file, krep.c:3818), so the driver start-up overlaps the host's own file handling; the first entry point
+ * that needs the GPU waits for it (and meanwhile pre-faults the caller's text with the staging threads). */
+void krep_b200_warmup(void);
 /* The devices a search_func_t call spreads the caller's text over — the analogue of krep's thread count
  * (krep.c:2851-2905 cuts the file into one chunk per pool thread; here into one contiguous range per GPU, each range
  * streamed over that GPU's own PCIe link and scanned there, per-device occurrence lists merged by key on the host).
@@ -292,6 +297,14 @@ uint64_t krep_b200_combine_line_counts(const krep_b200_line_count_t *recs, size_
  * Returns the count the reference would return. */
 uint64_t krep_b200_collect(const krep_b200_plan_t *plan, const search_params_t *params,
                            const krep_b200_device_result_t *dev, match_result_t *result);
+
+/* Several resident shards (text order; on one GPU or spread over the GPUs of this process), one answer: search_file's
+ * chunk loop and merge (krep.c:2851-3004) for text that already lives in HBM.  Shards on distinct devices are scanned
+ * concurrently, the per-shard lists merged by key, and the policy replayed ONCE over the whole list, so overlap rules,
+ * -m and the emission order are those of the reference's single-chunk run.  -c is answered by the fused line count
+ * (single literals; line cuts between shards are resolved). */
+uint64_t krep_b200_search_shards(const krep_b200_plan_t *plan, const search_params_t *params,
+                                 const krep_b200_shard_t *shards, uint32_t n_shards, match_result_t *result);
 
 /* Policy replay over a caller-supplied, ascending occurrence-key list in HOST memory (what
  * krep_b200_collect does after reading the device list back).  A multi-GPU host gathers the

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include "common.h"
 #include "corpus.h"
 #include "engine.h"
@@ -86,8 +87,40 @@ void trace(const char *fmt, ...)
     fprintf(stderr, "[krep_b200 +%.1f ms] %s\n", ms, buf);
 }
 
+// Asynchronous start-up (krep_b200_warmup): CUDA initialisation and the primary context are created on a background
+// thread while the host is still busy opening and mapping its file; the first entry point that needs the GPU joins it.
+static std::thread *g_warm = nullptr; // heap object on purpose: never destroyed behind a still-running thread
+static std::mutex g_warm_mu;
+void warm_join()
+{
+    std::lock_guard<std::mutex> lk(g_warm_mu);
+    if (g_warm && g_warm->joinable() && g_warm->get_id() != std::this_thread::get_id()) g_warm->join();
+}
+bool warm_running()
+{
+    std::lock_guard<std::mutex> lk(g_warm_mu);
+    return g_warm && g_warm->joinable();
+}
+static void warm_start()
+{
+    std::lock_guard<std::mutex> lk(g_warm_mu);
+    if (g_warm || g_visible >= 0) return; // already started, or CUDA is already up
+    g_warm = new std::thread([] {
+        trace("warm-up thread: start");
+        if (visible_devices() > 0) ctx_primary();
+        trace("warm-up thread: done");
+    });
+}
+__attribute__((destructor)) static void warm_at_exit()
+{
+    warm_join(); // a process that exits without searching must not tear CUDA down under the thread
+}
+
 int visible_devices()
 {
+    if (g_visible >= 0) return g_visible;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
     if (g_visible >= 0) return g_visible;
     int n = 0;
     trace("cudaGetDeviceCount ...");
@@ -910,6 +943,7 @@ extern "C" {
 
 int krep_b200_init(int device)
 {
+    warm_join();
     std::lock_guard<std::recursive_mutex> lk(engine_mutex());
     clear_error();
     if (visible_devices() == 0)
@@ -930,7 +964,12 @@ void krep_b200_shutdown(void) { engine_shutdown(); }
 int krep_b200_last_error(void) { return t_err; }
 const char *krep_b200_last_error_string(void) { return t_errmsg; }
 const char *krep_b200_version(void) { return "krep_b200 0.2.0 (sm_100a)"; }
-int krep_b200_device_count(void) { return visible_devices(); }
+int krep_b200_device_count(void)
+{
+    warm_join();
+    return visible_devices();
+}
+void krep_b200_warmup(void) { warm_start(); }
 
 float krep_b200_last_kernel_ms(void) { return t_kernel_ms; }
 uint64_t krep_b200_launch_count(void) { return g_launches; }
@@ -938,6 +977,7 @@ void krep_b200_reset_launch_count(void) { g_launches = 0; }
 
 krep_b200_plan_t *krep_b200_plan_create(const search_params_t *params, int algo)
 {
+    warm_join();
     std::lock_guard<std::recursive_mutex> lk(engine_mutex());
     clear_error();
     if (!params) return nullptr;

@@ -88,6 +88,8 @@ int visible_devices();           // cudaGetDeviceCount (0 when CUDA is unusable)
 DevCtx *ctx_get(int device);     // creates the context on first use; nullptr after set_error
 DevCtx *ctx_primary();           // ctx_get(primary_device())
 void engine_shutdown();
+void warm_join();    // waits for the krep_b200_warmup thread, if one is running
+bool warm_running();
 
 struct DeviceGuard // restores the calling thread's current device
 {

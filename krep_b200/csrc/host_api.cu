@@ -648,6 +648,22 @@ static uint64_t run_search(int entry_algo, const search_params_t *P, const char 
     int algo = entry_algo;
     uint64_t early = 0;
     if (early_answer(entry_algo, P, text, n, res, &algo, &early)) return early;
+    if (warm_running())
+    {
+        // the context is still being created on the warm-up thread: meanwhile fault the caller's pages in (a file the
+        // host mapped without MAP_POPULATE) with the staging threads, so that the copy loop later runs at link speed
+        if (n >= (64u << 20) && !getenv("KREP_B200_NO_PREFAULT"))
+        {
+            trace("search: pre-faulting %zu bytes while the context comes up", n);
+            const long pages = (long)((n + 4095) / 4096);
+            unsigned long sink = 0;
+#pragma omp parallel for num_threads(copy_threads()) schedule(static) reduction(+ : sink)
+            for (long pg = 0; pg < pages; pg++) sink += (unsigned char)text[(size_t)pg * 4096];
+            if (sink == 0x5EED5EED5EEDull) trace("(unlikely checksum)");
+        }
+        warm_join();
+        trace("search: context ready");
+    }
     if (visible_devices() == 0)
     {
         set_error(-1, "no CUDA device available; this engine has no CPU fallback");
@@ -683,6 +699,7 @@ static uint64_t run_search(int entry_algo, const search_params_t *P, const char 
 static int run_batch(int entry_algo, const search_params_t *P, const char *const *texts, const size_t *lens, size_t nt,
                      uint64_t *counts, match_result_t *const *results)
 {
+    warm_join();
     std::lock_guard<std::recursive_mutex> lk(engine_mutex());
     clear_error();
     if (!P || !texts || !lens || !counts)
@@ -914,6 +931,7 @@ const char *krep_b200_get_algorithm_name(search_func_t f)
 // ---- AC trie handles (aho_corasick.c:111 / 274 / 287) ----
 ac_trie_t *krep_b200_ac_trie_build(const search_params_t *params)
 {
+    warm_join();
     std::lock_guard<std::recursive_mutex> lk(engine_mutex());
     clear_error();
     if (!params || params->num_patterns == 0) return NULL; // aho_corasick.c:113
@@ -1072,6 +1090,112 @@ uint64_t krep_b200_combine_line_counts(const krep_b200_line_count_t *recs, size_
         flat[2 * i + 1] = recs[i].flags;
     }
     return std::min<uint64_t>(combine_line_records(flat.data(), n), max_count);
+}
+
+// ---- several resident shards, one answer: search_file's chunk loop + merge (krep.c:2851-3004) for text that already
+// lives in HBM, possibly on several GPUs of this process.  Scans run concurrently on distinct devices; per-shard lists are
+// merged by key; the emulated kernel's policy is replayed once over the whole list (so -m, overlap rules and the
+// emission order are global, not per shard).
+uint64_t krep_b200_search_shards(const krep_b200_plan_t *plan_, const search_params_t *P, const krep_b200_shard_t *shards,
+                                 uint32_t n_shards, match_result_t *result)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    clear_error();
+    const Plan *plan = reinterpret_cast<const Plan *>(plan_);
+    if (!plan || !P || (!shards && n_shards))
+    {
+        set_error(-3, "krep_b200_search_shards: null argument");
+        return 0;
+    }
+    DeviceGuard guard;
+    std::vector<DevCtx *> ctx(n_shards, nullptr);
+    uint64_t text_len = 0;
+    for (uint32_t i = 0; i < n_shards; i++)
+    {
+        cudaPointerAttributes a;
+        ctx[i] = (cudaPointerGetAttributes(&a, shards[i].d_text) == cudaSuccess && a.type == cudaMemoryTypeDevice) ? ctx_get(a.device)
+                                                                                                                    : ctx_primary();
+        if (!ctx[i]) return 0;
+        text_len = std::max<uint64_t>(text_len, shards[i].global_offset + shards[i].avail_len);
+    }
+    reset_kernel_ms();
+    if (P->count_lines_mode)
+    {
+        if (!count_lines_eligible(plan, P, plan->algo))
+        {
+            set_error(-3, "krep_b200_search_shards: -c over several shards is only available where the scan counts lines itself "
+                          "(single literals; see krep_b200_count_lines_shard)");
+            return 0;
+        }
+        if (P->max_count == 0) return 0;
+        std::vector<uint64_t> recs(2 * (size_t)n_shards);
+        for (uint32_t i = 0; i < n_shards; i++)
+            if (launch_count_lines(*ctx[i], plan, &shards[i], ctx[i]->scan_stream, i) != 0) return 0;
+        for (uint32_t i = 0; i < n_shards; i++)
+        {
+            cudaSetDevice(ctx[i]->device);
+            if (cudaStreamSynchronize(ctx[i]->scan_stream) != cudaSuccess)
+            {
+                set_error(-2, "CUDA error in the fused line count (%s)", cudaGetErrorString(cudaGetLastError()));
+                return 0;
+            }
+            recs[2 * i] = ctx[i]->h_line_out[2 * i];
+            recs[2 * i + 1] = ctx[i]->h_line_out[2 * i + 1];
+        }
+        return std::min<uint64_t>(combine_line_records(recs.data(), n_shards), P->max_count);
+    }
+    const bool need_list = (P->track_positions && result) || !keeps_all(plan->algo, plan->built_only_matching, P, plan) || plan->whole_word == 2;
+    std::vector<std::vector<uint64_t>> keys(n_shards);
+    std::vector<int> pending(MAX_DEV, -1); // shard whose scan is in flight on each device
+    std::vector<int> slot_of(n_shards, 0);
+    uint64_t total_count = 0;
+    float kmax = 0.f;
+    auto finish = [&](int i) -> int {
+        DevCtx &C = *ctx[i];
+        cudaSetDevice(C.device);
+        ScanOut so;
+        int rc = scan_end(C, slot_of[i], &so);
+        kmax = std::max(kmax, get_kernel_ms());
+        if (rc != 0) return rc;
+        total_count += so.count;
+        if (need_list && so.stored)
+        {
+            const uint64_t *k = nullptr;
+            if ((rc = fetch_keys(C, so, &k)) != 0) return rc;
+            keys[i].assign(k, k + so.stored);
+        }
+        return 0;
+    };
+    for (uint32_t i = 0; i < n_shards; i++)
+    {
+        DevCtx &C = *ctx[i];
+        if (pending[C.device] >= 0)
+        {
+            if (finish(pending[C.device]) != 0) return 0;
+            pending[C.device] = -1;
+        }
+        cudaSetDevice(C.device);
+        if (scan_begin(C, plan, &shards[i], need_list ? 1 : 0, nullptr, &slot_of[i]) != 0) return 0;
+        pending[C.device] = (int)i;
+    }
+    for (int d = 0; d < MAX_DEV; d++)
+        if (pending[d] >= 0 && finish(pending[d]) != 0) return 0;
+    set_kernel_ms(kmax);
+    if (!need_list) return limited_count(plan->algo, P, total_count);
+    std::vector<const uint64_t *> lists;
+    std::vector<uint64_t> counts;
+    uint64_t total = 0;
+    for (auto &k : keys)
+    {
+        lists.push_back(k.data());
+        counts.push_back(k.size());
+        total += k.size();
+    }
+    std::vector<uint64_t> merged(total ? total : 1);
+    const uint64_t nk = merge_key_lists(lists.data(), counts.data(), (uint32_t)lists.size(), merged.data());
+    Replay r{merged.data(), (size_t)nk, nullptr, text_len ? (size_t)text_len : (SIZE_MAX >> 1), 0};
+    if (plan->is_ac) return replay_ac(P, r, result);
+    return replay_literal(plan->algo, P, plan->built_only_matching, plan->m, r, result);
 }
 
 // ---- shard result -> match_result_t under the emulated kernel's policy ----

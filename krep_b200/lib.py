@@ -93,6 +93,8 @@ def load():
     L.krep_b200_merge_keys.restype = C.c_uint64
     L.krep_b200_set_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
     L.krep_b200_device_count.restype = C.c_int
+    L.krep_b200_search_shards.argtypes = [C.c_void_p, C.POINTER(SearchParams), C.POINTER(Shard), C.c_uint32, C.POINTER(MatchResult)]
+    L.krep_b200_search_shards.restype = C.c_uint64
     L.krep_b200_export_keys.argtypes = [C.POINTER(DeviceResult), C.c_void_p, C.c_uint64, C.c_void_p]
     L.krep_b200_export_keys.restype = C.c_int
     L.krep_b200_last_kernel_ms.restype = C.c_float

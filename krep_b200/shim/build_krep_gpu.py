@@ -12,7 +12,9 @@ result is written to build/krep_gpu/ (git-ignored) and compiled with gcc against
      --algo globals into the library and returns the krep_b200_* function;
   3. search_file hands the whole file to ONE search call (krep.c:2765: the single-chunk branch) — the GPU
      does its own tiling, and the result is the reference's -t 1 result rather than its multi-thread
-     chunk-edge artefacts.
+     chunk-edge artefacts (SURVEY §8 a12);
+  4. main calls krep_b200_warmup() right before it starts searching (krep.c:3818), and the file is mapped
+     without MAP_POPULATE for literal searches (krep.c:2679): CUDA start-up overlaps the file handling.
 
 The output binary is build/krep_gpu/krep: same CLI, same output code, GPU scan.
 """
@@ -44,6 +46,14 @@ def patched_source():
     src = _replace_once(src, "    run_single_thread_inline = (actual_thread_count == 1);",
                         "    if (!current_params.use_regex)\n        actual_thread_count = 1; /* krep_b200: one call per file */\n"
                         "    run_single_thread_inline = (actual_thread_count == 1);", "the chunk count")
+    # 4. start-up: the GPU context comes up on a background thread while search_file opens and maps the file, and the
+    #    mapping is not pre-populated by one kernel thread (the library's staging threads fault it in, in parallel)
+    src = _replace_once(src, "    // --- Execute Search ---\n    int exit_code = 1;",
+                        "    if (!params.use_regex)\n        krep_b200_warmup(); /* krep_b200: context creation overlaps the file handling */\n"
+                        "    // --- Execute Search ---\n    int exit_code = 1;", "the warm-up call")
+    src = _replace_once(src, "int mmap_flags_populate = mmap_base_flags | MAP_POPULATE;",
+                        "int mmap_flags_populate = mmap_base_flags | (current_params.use_regex ? MAP_POPULATE : 0); /* krep_b200 */",
+                        "MAP_POPULATE")
     with open(os.path.join(HERE, "krep_b200_dispatch.inc")) as f:
         src += "\n" + f.read()
     return src

@@ -475,3 +475,63 @@ def test_count_lines_on_newline_aligned_shards():
         finally:
             p.struct.ac_trie = None
             L.krep_b200_plan_destroy(plan)
+
+
+def test_search_shards_one_call_over_resident_shards():
+    """krep_b200_search_shards: several resident shards (here on one GPU; on a multi-GPU box spread over the devices),
+    one merged, globally replayed answer — literal with overlap policy and -m, pattern set with straddling plants, -c."""
+    L = lib.load()
+    wl, pats, longs = _bench_pattern_set_with_nested_pairs()
+    n = 5 * (1 << 20) + 321
+    spec = lib.make_spec(91, 92, 1 << 15, wl["needle"], wl["flags"])
+    host = bytearray(lib.corpus_host(spec, 0, n))
+    ndev = torch.cuda.device_count()
+    for nsh in (1, 3, 8):
+        S = ((n + nsh - 1) // nsh + 15) // 16 * 16
+        for g in range(1, nsh):
+            p = longs[g % len(longs)]
+            host[g * S - 3:g * S - 3 + len(p)] = p
+            host[g * S - 40:g * S - 36] = b"abab"
+    host = bytes(host)
+    from krep_b200.abi import Shard
+    cases = [("aho_corasick", ALGO_AC, pats, dict()), ("aho_corasick", ALGO_AC, pats, dict(max_count=2)),
+             ("sse42", ALGO_SSE42, [b"abab"], dict()), ("boyer_moore", ALGO_BMH, [b"abab"], dict(max_count=5)),
+             ("boyer_moore", ALGO_BMH, [b"the"], dict(count=True)), ("boyer_moore", ALGO_BMH, [b"et"], dict(whole_word=True, count=True)),
+             ("boyer_moore", ALGO_BMH, [wl["needle"]], dict(track_positions=False))]
+    for func, algo, pp, opts in cases:
+        p = Params(pp, **opts)
+        if func == "aho_corasick":
+            p.struct.ac_trie = 1
+        plan = L.krep_b200_plan_create(p.ref(), algo)
+        lib.check(L)
+        try:
+            halo = max(map(len, pp)) + 1
+            for nsh in (1, 3, 8):
+                S = ((n + nsh - 1) // nsh + 15) // 16 * 16
+                shards = (Shard * nsh)()
+                keep = []
+                for g in range(nsh):
+                    b, e = g * S, min((g + 1) * S, n)
+                    avail = min(e + halo, n)
+                    with torch.cuda.device(g % ndev):
+                        buf = torch.empty(avail - b + 64, dtype=torch.uint8, device="cuda")
+                        buf[: avail - b] = torch.frombuffer(bytearray(host[b:avail]), dtype=torch.uint8).cuda()
+                        torch.cuda.synchronize()
+                    keep.append(buf)
+                    shards[g] = Shard(buf.data_ptr(), avail - b, 0, e - b, b, host[b - 1] if b else -1, host[avail] if avail < n else -1)
+                res = L.krep_b200_match_result_init(16)
+                cnt = L.krep_b200_search_shards(plan, p.ref(), shards, nsh, res)
+                lib.check(L)
+                r = res.contents
+                got = (int(cnt), [(r.positions[i].start_offset, r.positions[i].end_offset) for i in range(r.count)])
+                L.krep_b200_match_result_free(res)
+                p.struct.ac_trie = None
+                want = checker().run(func, Params(pp, **opts), host)
+                if func == "aho_corasick":
+                    p.struct.ac_trie = 1
+                if opts.get("track_positions") is False:
+                    want = (want[0], [])
+                assert got == want, (func, opts, nsh, got[0], want[0])
+        finally:
+            p.struct.ac_trie = None
+            L.krep_b200_plan_destroy(plan)
