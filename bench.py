@@ -679,7 +679,7 @@ def _main(out_stream):
         for name, total_gib in todo:
             total = int(total_gib * GIB) // (16 * world) * (16 * world)
             try:
-                r = R.run(name, total, args.side_steps, 3)
+                r = R.run(name, total, args.side_steps if (name, total_gib) in SIDE_WORKLOADS else 3, 3)
             except Exception as e:  # noqa: BLE001  (all ranks fail alike: sizes and code are identical)
                 r = {"error": str(e)} if rank == 0 else None
             R.release_last()

@@ -122,6 +122,18 @@ int visible_devices()
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
     if (g_visible >= 0) return g_visible;
+    // KREP_B200_LIMIT_VISIBLE=1: a one-shot process that will use k devices (KREP_B200_DEVICES, default 1) hides the
+    // others from the driver before CUDA initialises, if the user has not chosen a device set already — on an 8-GPU
+    // box cuInit enumerates every visible GPU (measured: profiles/r2_cli_timing.md)
+    if (getenv("KREP_B200_LIMIT_VISIBLE") && !getenv("CUDA_VISIBLE_DEVICES"))
+    {
+        const char *v = getenv("KREP_B200_DEVICES");
+        const int k = v && atoi(v) > 0 ? atoi(v) : 1;
+        std::string list;
+        for (int d = 0; d < k && d < MAX_DEV; d++) list += (d ? "," : "") + std::to_string(d);
+        setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
+        trace("CUDA_VISIBLE_DEVICES=%s", list.c_str());
+    }
     int n = 0;
     trace("cudaGetDeviceCount ...");
     cudaError_t e = cudaGetDeviceCount(&n);
