@@ -454,6 +454,50 @@ class Runner:
             res.contents.count = 0
             return L.krep_b200_collect(plan, params.ref(), C.byref(dev), res)
 
+        if count_only:
+            # -c: the fused line count (csrc/scan_count.cu) — only a (lines, flags) record leaves the GPU
+            assert world == 1, "the -c side workloads run at N = 1"
+            from krep_b200.abi import SIZE_MAX
+
+            class LineCount(C.Structure):
+                _fields_ = [("lines", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+            L.krep_b200_count_lines_shard.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Shard), C.c_void_p, C.POINTER(LineCount)]
+            L.krep_b200_count_lines_shard.restype = C.c_int
+            L.krep_b200_combine_line_counts.argtypes = [C.POINTER(LineCount), C.c_size_t, C.c_size_t]
+            L.krep_b200_combine_line_counts.restype = C.c_uint64
+            rec = LineCount()
+
+            def count_step():
+                rc = L.krep_b200_count_lines_shard(plan, params.ref(), C.byref(shard), self.sptr, C.byref(rec))
+                assert rc == 0, L.krep_b200_last_error_string()
+                state["total"] = L.krep_b200_combine_line_counts(C.byref(rec), 1, SIZE_MAX)
+                return L.krep_b200_last_kernel_ms()
+
+            for _ in range(max(warmup, 3)):
+                count_step()
+            L.krep_b200_reset_launch_count()
+            self.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            kernel_ms = [count_step() for _ in range(steps)]
+            e1.record(self.stream)
+            self.barrier()
+            step_ms = e0.elapsed_time(e1) / max(steps, 1)
+            k = sum(kernel_ms) / max(len(kernel_ms), 1)
+            peak, peak_src = peaks()
+            achieved = total_bytes / (k * 1e-3) / 1e9
+            self._last = dict(plan=plan, params=params, res=res, pats=pats, algo=algo, total=int(state["total"]),
+                              own=own, avail=avail, g0=g0, spec=spec, halo=halo)
+            return {"value": total_bytes / (step_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": step_ms, "steps": steps,
+                    "total_bytes": total_bytes, "bytes_per_gpu": total_bytes, "matches": int(state["total"]), "first_matches": [],
+                    "filter": L.krep_b200_plan_filter_name(plan).decode() + " + fused line count", "halo": halo,
+                    "kernel_ms": k, "kernel_ms_per_rank": [k], "ms_per_step_per_rank": [step_ms], "exchange_ms": 0.0,
+                    "exchange_ms_per_rank": [0.0], "rank0_host_ms_per_step": 0.0,
+                    "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                 "kernel_ms": k, "algorithmic_bytes_per_launch": total_bytes, "peak_source": peak_src, "traffic": None},
+                    "gpu_launches": int(L.krep_b200_launch_count())}
+
         def process(slot):
             """rank 0, N>1: merge the gathered rows by key and replay them into match_result_t."""
             t0 = time.perf_counter()
@@ -567,8 +611,25 @@ class Runner:
         world, rank = self.world, self.rank
         out = None
         if rank == 0:
+            # the whole text in pinned host memory; if the box cannot pin that much, a prefix of it (stated in the output)
+            want_bytes = total_bytes
+            try:
+                with open("/proc/meminfo") as f:
+                    avail_kb = next(int(ln.split()[1]) for ln in f if ln.startswith("MemAvailable"))
+                while total_bytes > (16 << 30) and total_bytes > avail_kb * 1024 // 2:
+                    total_bytes //= 2
+            except Exception:  # noqa: BLE001
+                pass
+            host = None
             t_alloc = time.perf_counter()
-            host = torch.empty(total_bytes, dtype=torch.uint8, pin_memory=True)
+            while host is None:
+                try:
+                    host = torch.empty(total_bytes, dtype=torch.uint8, pin_memory=True)
+                except RuntimeError:
+                    if total_bytes <= (1 << 30):
+                        raise
+                    total_bytes //= 2
+            total_bytes -= total_bytes % 16
             t_alloc = time.perf_counter() - t_alloc
             piece = min(self.text.numel() - 64, total_bytes) // 16 * 16
             for off in range(0, total_bytes, piece):     # materialise the whole corpus in host memory through GPU 0
@@ -600,7 +661,8 @@ class Runner:
                    "d2h_bytes_per_step": 8 * world + 8 * got, "ms_per_step": dt * 1e3, "steps": steps,
                    "api": lib.SEARCH_ENTRIES[entry] + "(params, pinned host text, len, match_result_t*) — one call, one process, "
                           f"{world} device(s) (krep_b200_set_devices)",
-                   "bytes": total_bytes, "matches": got, "agrees_with_device_path": got == last["total"],
+                   "bytes": total_bytes, "full_corpus": total_bytes == want_bytes, "matches": got,
+                   "agrees_with_device_path": (got == last["total"]) if total_bytes == want_bytes else None,
                    "scan_kernel_ms_slowest_device": float(L.krep_b200_last_kernel_ms()), "pinned_alloc_s": t_alloc}
             del host
         if world > 1:

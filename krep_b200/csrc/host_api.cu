@@ -1129,8 +1129,16 @@ uint64_t krep_b200_search_shards(const krep_b200_plan_t *plan_, const search_par
         }
         if (P->max_count == 0) return 0;
         std::vector<uint64_t> recs(2 * (size_t)n_shards);
+        for (uint32_t i = 0; i < n_shards; i++) // size every device's record array first: growing it later would move it
+        {
+            cudaSetDevice(ctx[i]->device);
+            if (ensure_line_out(*ctx[i], n_shards) != 0) return 0;
+        }
         for (uint32_t i = 0; i < n_shards; i++)
+        {
+            cudaSetDevice(ctx[i]->device);
             if (launch_count_lines(*ctx[i], plan, &shards[i], ctx[i]->scan_stream, i) != 0) return 0;
+        }
         for (uint32_t i = 0; i < n_shards; i++)
         {
             cudaSetDevice(ctx[i]->device);

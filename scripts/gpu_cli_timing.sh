@@ -31,6 +31,13 @@ for args in "-c qzXv9Kpw" "-c -o qzXv9Kpw" "-c -i QzXv" "-c -w needleneedle0016"
     echo "$bin $args : $(run $bin $args $F) | $(run $bin $args $F)"
   done
 done
+echo "# BASELINE configs[0]: krep --algo=bm -t 1 -c the on 100 000 000 bytes of the synthetic corpus (plumbing check)"
+head -c 100000000 $F > /dev/shm/krep_cfg1.txt
+a=$(oracle/_ref/krep --algo=bm -t 1 -c the /dev/shm/krep_cfg1.txt); b=$(build/krep_gpu/krep --algo=bm -c the /dev/shm/krep_cfg1.txt)
+echo "stock: $a   gpu-backed: $b   identical: $([ "${a##*:}" = "${b##*:}" ] && echo yes || echo NO)"
+echo "stock  --algo=bm -t 1 -c the : $(run oracle/_ref/krep --algo=bm -t 1 -c the /dev/shm/krep_cfg1.txt)"
+echo "gpu    --algo=bm      -c the : $(run build/krep_gpu/krep --algo=bm -c the /dev/shm/krep_cfg1.txt)"
+rm -f /dev/shm/krep_cfg1.txt
 echo "# phase trace of one GPU-backed run (KREP_B200_TRACE=1)"
 KREP_B200_TRACE=1 build/krep_gpu/krep -c qzXv9Kpw $F 2>&1 | tail -40
 } 2>&1 | tee $O/${TAG}_timing.txt

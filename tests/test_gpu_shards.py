@@ -535,3 +535,61 @@ def test_search_shards_one_call_over_resident_shards():
         finally:
             p.struct.ac_trie = None
             L.krep_b200_plan_destroy(plan)
+
+
+def _reference_on_tensor(func, params, host_tensor, n, with_result=True):
+    """The compiled reference's kernel function called in-process on a torch CPU tensor (no bytes copy)."""
+    chk = checker()
+    chk._set_o(bool(params.only_matching))
+    trie = None
+    if func == "aho_corasick":
+        trie = chk._acb(params.ref())
+        params.struct.ac_trie = trie
+    res = chk._new(16) if with_result else None
+    try:
+        cnt = chk.fn[func](params.ref(), C.cast(host_tensor.data_ptr(), C.c_char_p), n, res)
+        pos = []
+        if res:
+            r = res.contents
+            pos = [(r.positions[i].start_offset, r.positions[i].end_offset) for i in range(r.count)]
+        return int(cnt), pos
+    finally:
+        if res:
+            chk._free(res)
+        if trie:
+            chk._acf(trie)
+            params.struct.ac_trie = None
+        chk._set_o(False)
+
+
+@pytest.mark.parametrize("name,gib,func,algo", [
+    ("literal8", 4.0, "sse42", ALGO_SSE42),
+    ("word16", 1.0, "sse42", ALGO_SSE42),
+    ("icase4", 2.0, "boyer_moore", ALGO_BMH),
+    ("multi1000", 0.25, "aho_corasick", ALGO_AC),
+])
+def test_bench_workloads_equal_the_reference_on_the_synthetic_corpus(name, gib, func, algo):
+    """The bench workloads themselves (same corpus generator, seeds, needles, pattern set) against the compiled
+    reference's single-chunk run, position for position, at sizes the reference still finishes in seconds."""
+    import bench
+    L = lib.load()
+    wl = bench.WORKLOADS[name]
+    n = int(gib * (1 << 30)) + 4096 + 5
+    pats = bench.multi_patterns(wl["multi"], wl["needle"]) if wl.get("multi") else [wl["needle"]]
+    spec = lib.make_spec(bench.SEED, bench.PLANT_SEED, wl["period"], wl["needle"], wl["flags"])
+    dev = gu.device_corpus(spec, 0, n)
+    host = dev[:n].cpu()
+    p = Params(pats if wl.get("multi") else wl["needle"], **wl["opts"])
+    if func == "aho_corasick":
+        p.struct.ac_trie = 1
+    plan = L.krep_b200_plan_create(p.ref(), algo)
+    lib.check(L)
+    try:
+        got = gu.collect(plan, p, gu.scan(plan, dev, n))
+        p.struct.ac_trie = None
+        want = _reference_on_tensor(func, Params(pats if wl.get("multi") else wl["needle"], **wl["opts"]), host, n)
+        assert got == want, (name, got[0], want[0])
+        assert got[0] >= n // wl["period"] // 2 - 2
+    finally:
+        p.struct.ac_trie = None
+        L.krep_b200_plan_destroy(plan)
