@@ -42,6 +42,8 @@ WORKLOADS = {
                    desc="-w 16-byte literal, low hit rate (BASELINE configs[4])"),
     "multi1000": dict(needle=b"kqzvxjwpy", opts={}, flags=0, period=1 << 22, multi=1000,
                       desc="1000 patterns of 6-12 bytes (-f), Aho-Corasick result set (BASELINE configs[3])"),
+    "multi1000_5to12": dict(needle=b"kqzvxjwpy", opts={}, flags=0, period=1 << 22, multi=1000, lens=(5, 12),
+                            desc="1000 patterns of 5-12 bytes (-f): shortest pattern 5, stride-2 paired filter (k_ac_scan)"),
     # hit-density workloads (not BASELINE configs): config 1's pattern `the`, planted once per 1 KiB / 64 B
     "the_1k": dict(needle=b"the", opts={}, flags=0, period=1 << 10,
                    desc="3-byte literal `the`, one planted per 1 KiB (plus accidental hits), count + all offsets"),
@@ -61,7 +63,7 @@ SEED, PLANT_SEED = 0x5EED0001, 0x5EED0002
 # BASELINE configs[2..4]: (workload, TOTAL GiB over all GPUs) — strong scaling over the N the run is launched with
 SIDE_WORKLOADS = [("icase4", 50.0), ("multi1000", 20.0), ("word16", 100.0)]
 # at N = 1 only: hit-density sweep on 10 GiB
-DENSITY_WORKLOADS = [("the_1k", 10.0), ("the_64", 10.0), ("the_1k_c", 10.0), ("the_64_c", 10.0)]
+DENSITY_WORKLOADS = [("the_1k", 10.0), ("the_64", 10.0), ("the_1k_c", 10.0), ("the_64_c", 10.0), ("multi1000_5to12", 10.0)]
 
 
 def peaks():

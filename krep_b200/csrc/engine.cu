@@ -107,7 +107,8 @@ static void warm_start()
     if (g_warm || g_visible >= 0) return; // already started, or CUDA is already up
     g_warm = new std::thread([] {
         trace("warm-up thread: start");
-        if (visible_devices() > 0) ctx_primary();
+        if (visible_devices() > 0)
+            if (DevCtx *C = ctx_primary()) prewarm_host_path(*C);
         trace("warm-up thread: done");
     });
 }

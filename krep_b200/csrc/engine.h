@@ -88,6 +88,7 @@ int visible_devices();           // cudaGetDeviceCount (0 when CUDA is unusable)
 DevCtx *ctx_get(int device);     // creates the context on first use; nullptr after set_error
 DevCtx *ctx_primary();           // ctx_get(primary_device())
 void engine_shutdown();
+void prewarm_host_path(DevCtx &C); // host_api.cu: rings + occurrence list for the pageable-text path
 void warm_join();    // waits for the krep_b200_warmup thread, if one is running
 bool warm_running();
 

@@ -233,6 +233,14 @@ static bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
+// Called by the warm-up thread once the context exists: the buffers a search on pageable host text (krep's mmap) will
+// ask for — device ring, pinned staging ring, occurrence list — are allocated while the host is still opening its file.
+void prewarm_host_path(DevCtx &E)
+{
+    const size_t slot = env_mb("KREP_B200_STAGE_MB", 32) + 4096; // chunk + the longest possible halo (1025) + slack
+    if (ensure_ring(E, slot, 3) != 0 || ensure_stage(E, slot, 3) != 0 || ensure_keys(E, 1) != 0) clear_error();
+}
+
 // One device's share of a search call: global bytes [begin, end) of the caller's text (end - begin a multiple of the
 // chunk size except for the last device), streamed chunk by chunk — host (pinned directly, pageable through the pinned
 // staging ring filled by host threads) -> copy stream -> ring slot -> scan stream — every chunk owning the starts in

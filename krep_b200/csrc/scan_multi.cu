@@ -459,6 +459,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_ac_scan(const __grid_constant__ 
             touch(v[u], nx[u]);
         }
         const uint64_t gn = g0 + stride;
+        // HBM latency comes off the registers: every warp bulk-prefetches its 1/(THREADS/32) share of the CTA tile that
+        // is PF iterations ahead of the register double buffer into L2 (one instruction per warp and tile)
+        if (A.pf_dist != 0 && lane == 0)
+        {
+            const uint64_t gp = gn + (uint64_t)A.pf_dist * stride;
+            if (gp + tile <= A.group_end)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t4 + gp + (uint64_t)warp * (tile / (THREADS / 32))),
+                             "r"((uint32_t)(tile / (THREADS / 32) * 16)) : "memory");
+        }
         if (gn + tile <= A.group_end)
         {
 #pragma unroll
@@ -1155,6 +1164,15 @@ void launch_ac(const Plan *plan, const AcDevTables *T, const AcLaunch &a, int sm
         return;
     }
     constexpr int THREADS = 640, UNROLL = 4;
+    {
+        static int pf = -1;
+        if (pf < 0)
+        {
+            const char *v = getenv("KREP_B200_AC_PF");
+            pf = v ? atoi(v) : 4;
+        }
+        A.pf_dist = (uint32_t)pf;
+    }
     const size_t smem = (size_t)T->bitmap_bytes + 128 + (size_t)(THREADS / 32) * AcQueue<UNROLL>::CAP * sizeof(uint64_t);
     auto kernel = [&]() -> void (*)(AcDev) {
         const bool f = T->fold != 0xFFFFFFFFu;
