@@ -518,11 +518,11 @@ class Runner:
             assert rc == 0, L.krep_b200_last_error_string()
             return L.krep_b200_last_kernel_ms()
 
-        ticket = C.c_int(0)
+        tickets = [C.c_int(0), C.c_int(0)]
         # warm-up (N>1: also sizes the exchange buffers on all ranks, collectively)
         for _ in range(max(warmup, 3)):
-            scan(ticket)
-            end(ticket)
+            scan(tickets[0])
+            end(tickets[0])
             if world == 1:
                 state["total"] = finish_single()
             else:
@@ -532,6 +532,15 @@ class Runner:
                 g.post(0)
                 if rank == 0:
                     process(0)
+        # Lists that come back packed with the count (<= 16384 occurrences on every rank) let the steps overlap: scan
+        # i+1 (and, N>1, its export + gather) is enqueued before the host waits for scan i, so the GPU runs back to
+        # back and all host work of step i (replay; on rank 0 the key merge too) happens while step i+1 scans.
+        fits = 1 if int(dev.stored) <= min(16384, g.cap if g else 16384) else 0
+        if world > 1:
+            ft = torch.tensor([fits], dtype=torch.int64, device="cuda")
+            dist.all_reduce(ft, op=dist.ReduceOp.MIN)
+            fits = int(ft.item())
+        overlapped = bool(fits)
         L.krep_b200_reset_launch_count()
         state["host_ms"] = 0.0
         if sampler is not None and rank == 0:
@@ -543,21 +552,44 @@ class Runner:
         xa = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         xb = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         kernel_ms = []
-        e0.record(self.stream)
-        for i in range(steps):
-            scan(ticket)                                   # enqueue scan i
-            if world > 1 and rank == 0 and i > 0:
-                process((i - 1) & 1)                       # host work of step i-1 while scan i runs
-            kernel_ms.append(end(ticket))                  # the step's one synchronisation
-            if world == 1:
-                state["total"] = finish_single()
-            else:
+
+        def launch(i):
+            """Everything of step i that runs on the GPU, enqueued without waiting."""
+            scan(tickets[i & 1])
+            if world > 1:
                 xa[i].record(self.stream)
-                L.krep_b200_export_packed(C.byref(dev), g.row_ptr(), g.cap, self.sptr)
+                rc = L.krep_b200_export_packed_async(tickets[i & 1].value, g.row_ptr(), g.cap)
+                assert rc == 0, L.krep_b200_last_error_string()
                 g.post(i & 1)
                 xb[i].record(self.stream)
-        if world > 1 and rank == 0 and steps:
-            process((steps - 1) & 1)
+
+        e0.record(self.stream)
+        if overlapped:
+            if steps:
+                launch(0)
+            for i in range(steps):
+                if i + 1 < steps:
+                    launch(i + 1)
+                kernel_ms.append(end(tickets[i & 1]))      # waits for scan i only
+                if world == 1:
+                    state["total"] = finish_single()
+                elif rank == 0:
+                    process(i & 1)
+        else:
+            for i in range(steps):
+                scan(tickets[0])
+                if world > 1 and rank == 0 and i > 0:
+                    process((i - 1) & 1)                   # host work of step i-1 while scan i runs
+                kernel_ms.append(end(tickets[0]))
+                if world == 1:
+                    state["total"] = finish_single()
+                else:
+                    xa[i].record(self.stream)
+                    L.krep_b200_export_packed(C.byref(dev), g.row_ptr(), g.cap, self.sptr)
+                    g.post(i & 1)
+                    xb[i].record(self.stream)
+            if world > 1 and rank == 0 and steps:
+                process((steps - 1) & 1)
         e1.record(self.stream)
         self.barrier()
         if sampler is not None:
@@ -585,6 +617,7 @@ class Runner:
                 "filter": L.krep_b200_plan_filter_name(plan).decode(), "halo": halo,
                 "kernel_ms": k_max, "kernel_ms_per_rank": k_all, "ms_per_step_per_rank": step_all,
                 "exchange_ms": x_max, "exchange_ms_per_rank": x_all, "rank0_host_ms_per_step": state["host_ms"] / max(steps, 1),
+                "steps_overlapped": overlapped,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "kernel_ms": k_max, "algorithmic_bytes_per_launch": int(per_gpu), "peak_source": peak_src,
                              "traffic": measured_traffic(name, per_gpu)},

@@ -237,7 +237,9 @@ int krep_b200_scan_shard(const krep_b200_plan_t *plan, const krep_b200_shard_t *
                          int want_positions, void *stream, krep_b200_device_result_t *out);
 /* The same scan in two halves: _begin enqueues it and returns a ticket without waiting, _end waits for it.  A host
  * that has work of its own per scan (rank 0 of a multi-GPU job replaying the previous step's gathered list) does it
- * between the two.  At most two scans per device may be in flight. */
+ * between the two.  At most two scans per device may be in flight, and _end only waits for its own scan: a host that
+ * begins scan i+1 before it ends scan i keeps the GPU busy back to back (lists of up to 16 384 occurrences, which come
+ * back through pinned memory; a longer list must be ended before the next scan begins). */
 int krep_b200_scan_shard_begin(const krep_b200_plan_t *plan, const krep_b200_shard_t *shard,
                                int want_positions, void *stream, int *ticket);
 int krep_b200_scan_shard_end(int ticket, krep_b200_device_result_t *out);
@@ -248,6 +250,9 @@ int krep_b200_export_keys(const krep_b200_device_result_t *dev, void *d_dst, uin
 /* The row a multi-GPU host gathers: d_dst[0] = the shard's exact occurrence count, d_dst[1..] = its first
  * min(stored, max_keys) sorted keys — one device-to-device copy on `stream`. */
 int krep_b200_export_packed(const krep_b200_device_result_t *dev, void *d_dst, uint64_t max_keys, void *stream);
+/* The same row for a scan that is still in flight (its ticket): enqueued on the scan's stream behind the finish kernel,
+ * always the whole fixed-size row (max_keys <= 16384); a longer list arrives as count > max_keys. */
+int krep_b200_export_packed_async(int ticket, void *d_dst, uint64_t max_keys);
 /* Merge step of a sharded search (krep.c:2928-3004 without its chunk-edge artefacts): n_lists ascending key lists
  * (one per shard, shards in text order) -> one ascending list in dst (room for the sum of counts; may alias the
  * first list).  Literal keys (ordered and owned by start offset) are already globally ordered after concatenation;

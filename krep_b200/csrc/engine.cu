@@ -115,6 +115,7 @@ static void warm_start()
 __attribute__((destructor)) static void warm_at_exit()
 {
     warm_join(); // a process that exits without searching must not tear CUDA down under the thread
+    trace("library destructor (process exit)");
 }
 
 int visible_devices()
@@ -188,6 +189,7 @@ static int ctx_create(DevCtx &E, int device)
         E.h_pack[s][0] = 0;
         CK(cudaEventCreate(&E.ev_a[s]));
         CK(cudaEventCreate(&E.ev_b[s]));
+        CK(cudaEventCreateWithFlags(&E.ev_done[s], cudaEventDisableTiming));
     }
     E.ready = true;
     trace("device %d: context ready (%s, %d SMs)", device, prop.name, E.sm_count);
@@ -246,6 +248,7 @@ static void ctx_destroy(DevCtx &E)
         cudaFreeHost(E.h_pack[s]);
         cudaEventDestroy(E.ev_a[s]);
         cudaEventDestroy(E.ev_b[s]);
+        cudaEventDestroy(E.ev_done[s]);
     }
     for (auto &s : E.stage) cudaFreeHost(s.buf);
     for (auto &s : E.stage)
@@ -629,6 +632,7 @@ int finish_scan(DevCtx &E, int slot, int want_sort, cudaStream_t stream)
     k_finish<<<1, 1024, smem, stream>>>(E.d_counter, E.d_keys[0], E.key_cap, E.d_pack[slot], E.h_pack[slot],
                                         (want_sort && E.d_keys[0]) ? 1 : 0);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(E.ev_done[slot], stream));
     count_launch();
     E.counter_clean = true;
     return 0;
@@ -807,10 +811,13 @@ int scan_end(DevCtx &E, int slot, ScanOut *out)
     const Plan *plan = P.plan;
     const krep_b200_shard_t *sh = &P.shard;
     cudaStream_t stream = P.stream;
+    bool later_scan = false; // a scan begun after this one is in flight: it appends to the same device list
+    for (int s2 = 0; s2 < SCAN_SLOTS; s2++) later_scan |= s2 != slot && E.pend[s2].active;
     reset_kernel_ms();
     for (int attempt = 0; attempt < 3; attempt++)
     {
-        CK(cudaStreamSynchronize(stream));
+        // wait for this scan's k_finish only (not for the stream: the next scan may already be running behind it)
+        CK(cudaEventSynchronize(E.ev_done[slot]));
         const uint64_t cnt = E.h_pack[slot][0];
         float ms = 0.f;
         cudaEventElapsedTime(&ms, E.ev_a[slot], E.ev_b[slot]);
@@ -821,17 +828,33 @@ int scan_end(DevCtx &E, int slot, ScanOut *out)
         out->serial = ++E.serial;
         E.result_stream = stream;
         if (!P.want_positions) return 0;
+        if (cnt <= PACK_KEYS && cnt <= E.key_cap)
+        {
+            out->stored = cnt;
+            out->d_keys = later_scan ? nullptr : E.d_keys[0]; // the device list is only intact when nothing ran behind it
+            out->h_sorted = E.h_pack[slot] + 1;
+            if (plan->count_lines && cnt)
+            {
+                if (later_scan)
+                {
+                    set_error(-3, "krep_b200_scan_shard_end: -c plans need the device list: end the scan before beginning the next");
+                    return -3;
+                }
+                return line_bounds(E, plan, sh, out->d_keys, cnt, stream, &out->d_bounds);
+            }
+            return 0;
+        }
+        if (later_scan)
+        {
+            set_error(-3, "krep_b200_scan_shard_end: %llu occurrences do not fit the packed read-back (%u) and another scan is "
+                          "already in flight behind this one: end each scan before beginning the next for lists this long",
+                      (unsigned long long)cnt, PACK_KEYS);
+            return -3;
+        }
         if (cnt <= E.key_cap)
         {
-            int rc = 0;
             out->stored = cnt;
-            if (cnt <= PACK_KEYS)
-            {
-                out->d_keys = E.d_keys[0];
-                out->h_sorted = E.h_pack[slot] + 1;
-            }
-            else
-                rc = sort_keys(E, cnt, key_end_bit(plan, sh->global_offset + sh->avail_len), stream, &out->d_keys);
+            int rc = sort_keys(E, cnt, key_end_bit(plan, sh->global_offset + sh->avail_len), stream, &out->d_keys);
             if (rc == 0 && plan->count_lines) rc = line_bounds(E, plan, sh, out->d_keys, cnt, stream, &out->d_bounds);
             return rc;
         }
@@ -1122,6 +1145,33 @@ int krep_b200_export_packed(const krep_b200_device_result_t *dev, void *d_dst, u
         if (n) CK(cudaMemcpyAsync((uint64_t *)d_dst + 1, dev->d_keys, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
     }
     if (!stream) CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// The same row for a scan that is still in flight (ticket of krep_b200_scan_shard_begin): enqueued on the scan's own
+// stream behind its finish kernel, so the host does not have to know the count first — the whole fixed-size row
+// [count, key_0 .. key_{max_keys-1}] is copied (max_keys <= 16384: only lists that short are sorted by the finish kernel;
+// a longer list shows up at the receiver as count > max_keys).
+int krep_b200_export_packed_async(int ticket, void *d_dst, uint64_t max_keys)
+{
+    std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    clear_error();
+    if (!d_dst || ticket < 0 || ticket >= MAX_DEV * SCAN_SLOTS || max_keys > PACK_KEYS)
+    {
+        set_error(-3, "krep_b200_export_packed_async: bad argument");
+        return -3;
+    }
+    DeviceGuard guard;
+    DevCtx *C = ctx_get(ticket / SCAN_SLOTS);
+    if (!C) return -1;
+    const int slot = ticket % SCAN_SLOTS;
+    if (!C->pend[slot].active)
+    {
+        set_error(-3, "krep_b200_export_packed_async: no scan in flight for this ticket");
+        return -3;
+    }
+    cudaStream_t s = C->pend[slot].stream;
+    CK(cudaMemcpyAsync(d_dst, C->d_pack[slot], (max_keys + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
     return 0;
 }
 

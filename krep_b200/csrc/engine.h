@@ -51,6 +51,7 @@ struct DevCtx
     // the finish kernel writes through, d_pack the device copy that krep_b200_export_packed hands to a collective
     uint64_t *d_pack[SCAN_SLOTS] = {nullptr, nullptr}, *h_pack[SCAN_SLOTS] = {nullptr, nullptr};
     cudaEvent_t ev_a[SCAN_SLOTS] = {nullptr, nullptr}, ev_b[SCAN_SLOTS] = {nullptr, nullptr};
+    cudaEvent_t ev_done[SCAN_SLOTS] = {nullptr, nullptr}; // recorded after k_finish: what scan_end waits for
     PendingScan pend[SCAN_SLOTS];
     int next_slot = 0;
     uint64_t serial = 0;

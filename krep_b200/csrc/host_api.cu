@@ -499,6 +499,7 @@ static int stage_and_scan(const Plan *plan, const char *text, size_t n, int want
         }
         set_kernel_ms(*std::max_element(kdev.begin(), kdev.end())); // devices scan concurrently: the slowest one's time
     }
+    trace("search: all ranges scanned (slowest device: %.2f ms of scan kernels)", get_kernel_ms());
     hs->count = 0;
     hs->keys = nullptr;
     hs->nkeys = 0;
@@ -660,7 +661,9 @@ static uint64_t run_search(int entry_algo, const search_params_t *P, const char 
     {
         // the context is still being created on the warm-up thread: meanwhile fault the caller's pages in (a file the
         // host mapped without MAP_POPULATE) with the staging threads, so that the copy loop later runs at link speed
-        if (n >= (64u << 20) && !getenv("KREP_B200_NO_PREFAULT"))
+        // (opt-in: measured on the bench box, faulting pages in the same process while cuInit / context creation run
+        // more than doubles their time — both sides fight over the address-space lock; profiles/r2b_cli_timing.txt)
+        if (n >= (64u << 20) && getenv("KREP_B200_PREFAULT"))
         {
             trace("search: pre-faulting %zu bytes while the context comes up", n);
             const long pages = (long)((n + 4095) / 4096);

@@ -50,6 +50,7 @@ struct CountDev
     LitDevParams p;
     uint64_t own_end; // min(shard own_end, avail_len)
     uint32_t part_groups, n_parts;
+    uint32_t exact;   // the window filter decides by itself (<= 4 pattern bytes under an exact mask, no -w): no verify loads
     uint32_t tail;    // the vector groups stop short of the owned range (end of the buffer): the last partition's warp
                       // also walks the bytes behind them
     LineRec *recs;
@@ -184,14 +185,36 @@ __device__ __forceinline__ void account(PartState &S, uint32_t hm, uint32_t nm)
     }
 }
 
-// One 512-byte vector with at least one filter candidate.  `unit` = byte position of this lane's 16 bytes (valid lanes only).
+// One 512-byte vector with at least one filter candidate.  `nlmask4` bit u' = vector u' of the current tile (which
+// starts at tile_lo) holds a newline — from the registers, valid when the whole tile lies inside the partition's newline
+// range (tile_inside); it settles "did the open line end in the skipped vectors of this tile" without touching memory.
 template <bool WINDOW>
 __device__ __noinline__ void count_vector(const CountDev &D, PartState &S, uint64_t vec_lo, bool valid, uint4 v, uint32_t nx,
-                                          uint64_t nl_lo, uint64_t nl_hi)
+                                          uint64_t nl_lo, uint64_t nl_hi, uint64_t tile_lo, uint32_t nlmask4, bool tile_inside)
 {
     const LitDevParams &p = D.p;
     const uint32_t lane = threadIdx.x & 31;
-    settle(p, S, vec_lo > nl_lo ? vec_lo : nl_lo);
+    {
+        const uint64_t upto = vec_lo > nl_lo ? vec_lo : nl_lo;
+        if (S.covered_to < upto && (S.pending || (!S.has_hit && !S.seen_nl)))
+        {
+            bool found = false;
+            if (tile_inside)
+            {
+#pragma unroll
+                for (int u2 = 0; u2 < 4; u2++)
+                    found |= ((nlmask4 >> u2) & 1u) && tile_lo + 512ull * u2 >= S.covered_to && tile_lo + 512ull * u2 < vec_lo;
+                if (!found && S.covered_to < tile_lo) found = scan_for_newline(p, S.covered_to, tile_lo);
+            }
+            else
+                found = scan_for_newline(p, S.covered_to, upto);
+            if (found)
+            {
+                S.pending = false;
+                S.seen_nl = true;
+            }
+        }
+    }
     const uint64_t unit = vec_lo + 16ull * lane;
     uint32_t hm = 0, nm = 0;
     if (valid)
@@ -206,7 +229,13 @@ __device__ __noinline__ void count_vector(const CountDev &D, PartState &S, uint6
                 for (int r = 0; r < 4; r++)
                 {
                     const uint32_t win = r == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * r);
-                    if ((win & mask) == k0 && verify_exact(p, (long long)(unit + 4 * k + r))) hm |= 1u << (4 * k + r);
+                    if ((win & mask) == k0)
+                    {
+                        const uint64_t st = unit + 4 * k + r;
+                        const bool ok = D.exact ? (st >= p.own_begin && st < p.own_end && st + p.m <= p.avail_len)
+                                                : verify_exact(p, (long long)st) != 0;
+                        if (ok) hm |= 1u << (4 * k + r);
+                    }
                 }
         }
         else
@@ -304,9 +333,20 @@ __global__ void __launch_bounds__(256, 3) k_count_lines(const __grid_constant__ 
             const uint32_t any = __reduce_or_sync(0xffffffffu, cand);
             if (any)
             {
+                const uint64_t tile_lo = g * 16;
+                const bool tile_inside = tile_lo >= nl_lo && tile_lo + 2048 <= nl_hi && g + 128 <= gb;
+                uint32_t nlmask4 = 0;
+                if (tile_inside)
+                {
+                    uint32_t mine = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) mine |= nl_mask16(v[u]) ? (1u << u) : 0u;
+                    nlmask4 = __reduce_or_sync(0xffffffffu, mine);
+                }
 #pragma unroll
                 for (int u = 0; u < 4; u++)
-                    if ((any >> u) & 1u) count_vector<WINDOW>(D, S, (g + 32 * u) * 16, ok[u], v[u], nx[u], nl_lo, nl_hi);
+                    if ((any >> u) & 1u)
+                        count_vector<WINDOW>(D, S, (g + 32 * u) * 16, ok[u], v[u], nx[u], nl_lo, nl_hi, tile_lo, nlmask4, tile_inside);
             }
         }
         if (last_part && D.tail) count_tail(D, S, gb * 16, nl_lo, nl_hi, WINDOW);
@@ -469,6 +509,11 @@ int launch_count_lines(DevCtx &E, const Plan *plan, const krep_b200_shard_t *sh,
     p.pat_mask = pd->d_pat_mask;
     p.whole_word = plan->whole_word;
     D.own_end = own_end;
+    {
+        bool letters = true;
+        for (unsigned char ch : plan->pattern) letters &= is_alpha_c(ch);
+        D.exact = (window && plan->m <= 4 && plan->whole_word == 0 && (plan->case_sensitive || letters)) ? 1u : 0u;
+    }
     const uint64_t groups = p.group_end - p.group_begin;
     static uint32_t part_default = 0;
     if (!part_default)

@@ -30,6 +30,10 @@
 #include "common.h"
 #include "lit_filters.cuh"
 
+#ifndef KREP_B200_WARP_EMIT
+#define KREP_B200_WARP_EMIT 1 // 1: warp-cooperative emission (one atomicAdd per warp and vector); 0: one per occurrence
+#endif
+
 namespace kb {
 
 // Exact check of one candidate start + emission. Out of line on purpose: keeps the streaming loop's
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(256, 4) k_lit_aligned4(const __grid_constant__
         bool hit = false;
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) hit |= hit_vec<FOLD>(v[u], fold, k0, k1, k2, k3);
+#if KREP_B200_WARP_EMIT
         if (__any_sync(0xffffffffu, hit)) // rare; the whole warp goes (full tiles: all 32 lanes are here)
         {
 #pragma unroll
@@ -180,6 +185,15 @@ __global__ void __launch_bounds__(256, 4) k_lit_aligned4(const __grid_constant__
                     local_cnt += emit_warp<false>(p, g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u], 0u, mine);
             }
         }
+#else
+        if (hit)
+        {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++)
+                if (hit_vec<FOLD>(v[u], fold, k0, k1, k2, k3))
+                    local_cnt += slow_aligned4(p, g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u]);
+        }
+#endif
     }
     if (g0 < p.group_end) // the one ragged tile
     {
@@ -215,6 +229,9 @@ __device__ __noinline__ unsigned slow_window4(const LitDevParams &p, uint64_t gr
 // Main loads of the window kernel: the sector that holds a warp's "next word" is touched twice (once as lane 31's
 // next-word load, once as the following warp's vector), so these loads keep the default L2 policy instead of
 // evict-first; KREP_B200_W4_CS=1 at build time restores the streaming hint for comparison.
+#ifndef KREP_B200_W4_NX
+#define KREP_B200_W4_NX 2 // how the window kernel gets the word behind a vector: 0 = every lane loads it, 1 / 2 = shuffle
+#endif
 #ifdef KREP_B200_W4_CS
 #define WLOAD(q) ld_stream(q)
 #else
@@ -240,20 +257,36 @@ __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ 
         {
             const uint4 *q = t4 + g0 + (uint64_t)u * blockDim.x + threadIdx.x;
             v[u] = WLOAD(q);
-            // the word after the vector is the next lane's v.x: only lane 31 has to load it (one sector per 512 bytes
-            // instead of one 4-byte request per lane)
+#if KREP_B200_W4_NX == 0
+            nx[u] = __ldg(reinterpret_cast<const uint32_t *>(q + 1)); // every lane loads its own next word (L1/L2 hit)
+#elif KREP_B200_W4_NX == 2
+            // the word after the vector is the next lane's v.x: only lane 31 has to load it — as ONE predicated
+            // instruction (a branch around the load would make the warp reconverge before every shuffle below)
+            nx[u] = 0u;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}"
+                         : "+r"(nx[u])
+                         : "l"(reinterpret_cast<const uint32_t *>(q + 1)), "r"((uint32_t)lane31));
+#else
             nx[u] = lane31 ? __ldg(reinterpret_cast<const uint32_t *>(q + 1)) : 0u;
+#endif
         }
+#if KREP_B200_W4_NX != 0
 #pragma unroll
         for (int u = 0; u < UNROLL; u++)
         {
             const uint32_t nb = __shfl_down_sync(0xffffffffu, v[u].x, 1);
+#if KREP_B200_W4_NX == 2
+            nx[u] = lane31 ? nx[u] : nb; // a select, not a branch
+#else
             if (!lane31) nx[u] = nb;
+#endif
         }
+#endif
         uint32_t hm = 0; // bit u: vector u holds a candidate
 #pragma unroll
         for (int u = 0; u < UNROLL; u++)
             hm |= hit_vec_w<FOLD, MASKED>(v[u], nx[u], fold, mask, k0, c1, c2, c3) ? (1u << u) : 0u;
+#if KREP_B200_WARP_EMIT
         const uint32_t anyhm = __reduce_or_sync(0xffffffffu, hm);
         if (anyhm)
         {
@@ -262,6 +295,14 @@ __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ 
                 if ((anyhm >> u) & 1u)
                     local_cnt += emit_warp<true>(p, g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u], nx[u], (hm >> u) & 1u);
         }
+#else
+        if (hm)
+        {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++)
+                if ((hm >> u) & 1u) local_cnt += slow_window4(p, g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u], nx[u]);
+        }
+#endif
     }
     if (g0 < p.group_end)
     {

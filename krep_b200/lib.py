@@ -10,7 +10,7 @@ import os
 from .abi import (CorpusSpec, DeviceResult, MatchResult, Params, SearchParams, Shard, SEARCH_FUNC, SIZE_MAX)  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkrep_b200.so")
+LIB_PATH = os.environ.get("KREP_B200_LIB") or os.path.join(_HERE, "libkrep_b200.so")  # override: kernel-variant builds
 
 SEARCH_ENTRIES = {
     "boyer_moore": "krep_b200_boyer_moore_search",
@@ -89,6 +89,8 @@ def load():
     L.krep_b200_scan_shard_end.restype = C.c_int
     L.krep_b200_export_packed.argtypes = [C.POINTER(DeviceResult), C.c_void_p, C.c_uint64, C.c_void_p]
     L.krep_b200_export_packed.restype = C.c_int
+    L.krep_b200_export_packed_async.argtypes = [C.c_int, C.c_void_p, C.c_uint64]
+    L.krep_b200_export_packed_async.restype = C.c_int
     L.krep_b200_merge_keys.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p]
     L.krep_b200_merge_keys.restype = C.c_uint64
     L.krep_b200_set_devices.argtypes = [C.POINTER(C.c_int), C.c_int]

@@ -52,7 +52,7 @@ def patched_source():
                         "    if (!params.use_regex)\n        krep_b200_warmup(); /* krep_b200: context creation overlaps the file handling */\n"
                         "    // --- Execute Search ---\n    int exit_code = 1;", "the warm-up call")
     src = _replace_once(src, "int mmap_flags_populate = mmap_base_flags | MAP_POPULATE;",
-                        "int mmap_flags_populate = mmap_base_flags | (current_params.use_regex ? MAP_POPULATE : 0); /* krep_b200 */",
+                        "int mmap_flags_populate = mmap_base_flags | ((current_params.use_regex || getenv(\"KREP_B200_MAP_POPULATE\")) ? MAP_POPULATE : 0); /* krep_b200 */",
                         "MAP_POPULATE")
     with open(os.path.join(HERE, "krep_b200_dispatch.inc")) as f:
         src += "\n" + f.read()

@@ -40,5 +40,27 @@ echo "gpu    --algo=bm      -c the : $(run build/krep_gpu/krep --algo=bm -c the 
 rm -f /dev/shm/krep_cfg1.txt
 echo "# phase trace of one GPU-backed run (KREP_B200_TRACE=1)"
 KREP_B200_TRACE=1 build/krep_gpu/krep -c qzXv9Kpw $F 2>&1 | tail -40
+KREP_B200_TRACE=1 build/krep_gpu/krep -c the $F 2>&1 | tail -12
+echo "# variants of the GPU-backed run: krep maps with MAP_POPULATE again / 16 staging threads / pages pre-faulted during start-up"
+for v in "KREP_B200_MAP_POPULATE=1" "KREP_B200_COPY_THREADS=16" "KREP_B200_PREFAULT=1"; do
+  echo "$v gpu -c qzXv9Kpw : $(env $v python - build/krep_gpu/krep -c qzXv9Kpw $F <<'PY'
+import subprocess, sys, time
+t0 = time.perf_counter(); r = subprocess.run(sys.argv[1:], capture_output=True); dt = time.perf_counter() - t0
+print(f"{dt:.3f} s rc={r.returncode}")
+PY
+)"
+done
+echo "# the same with the driver kept initialised by another process (what nvidia-persistenced / any resident CUDA client gives)"
+python -c "import torch, time; torch.zeros(1, device='cuda'); time.sleep(120)" &
+HOLD=$!; sleep 20
+build/cuinit_probe 1
+for args in "-c qzXv9Kpw" "-c -i QzXv" "-c -w needleneedle0016" "-c -o -f $P" "-c the"; do
+  echo "warm driver: stock $args : $(run oracle/_ref/krep $args $F)"
+  echo "warm driver: gpu   $args : $(run build/krep_gpu/krep $args $F) | $(run build/krep_gpu/krep $args $F)"
+done
+KREP_B200_TRACE=1 build/krep_gpu/krep -c qzXv9Kpw $F 2>&1 | tail -16
+KREP_B200_MAP_POPULATE=1 KREP_B200_TRACE=1 build/krep_gpu/krep -c qzXv9Kpw $F 2>&1 | tail -12
+echo "warm driver, MAP_POPULATE: gpu -c qzXv9Kpw : $(KREP_B200_MAP_POPULATE=1 run build/krep_gpu/krep -c qzXv9Kpw $F) | 16 threads: $(KREP_B200_COPY_THREADS=16 run build/krep_gpu/krep -c qzXv9Kpw $F)"
+kill $HOLD
 } 2>&1 | tee $O/${TAG}_timing.txt
 rm -f $F $P
