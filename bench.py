@@ -553,24 +553,27 @@ class Runner:
         xb = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         kernel_ms = []
 
-        def launch(i):
-            """Everything of step i that runs on the GPU, enqueued without waiting."""
-            scan(tickets[i & 1])
-            if world > 1:
-                xa[i].record(self.stream)
-                rc = L.krep_b200_export_packed_async(tickets[i & 1].value, g.row_ptr(), g.cap)
-                assert rc == 0, L.krep_b200_last_error_string()
-                g.post(i & 1)
-                xb[i].record(self.stream)
+        def exchange(i):
+            """N>1: row of step i -> rank 0 (enqueued behind whatever is already on the stream)."""
+            xa[i].record(self.stream)
+            rc = L.krep_b200_export_packed_async(tickets[i & 1].value, g.row_ptr(), g.cap)
+            assert rc == 0, L.krep_b200_last_error_string()
+            g.post(i & 1)
+            xb[i].record(self.stream)
 
         e0.record(self.stream)
         if overlapped:
-            if steps:
-                launch(0)
+            # software pipeline, two scans in flight: the stream always holds the next scan behind the current one; the
+            # finish kernel of scan i runs on the library's finish stream while scan i+1 scans; all host work of step i
+            # (N=1: replay; rank 0: key merge + replay) happens while scan i+2 is already queued
+            for i in range(min(2, steps)):
+                scan(tickets[i & 1])
             for i in range(steps):
-                if i + 1 < steps:
-                    launch(i + 1)
-                kernel_ms.append(end(tickets[i & 1]))      # waits for scan i only
+                if world > 1:
+                    exchange(i)
+                kernel_ms.append(end(tickets[i & 1]))      # waits for scan i's finish kernel only
+                if i + 2 < steps:
+                    scan(tickets[i & 1])                   # step i+2 into the slot that has just been ended
                 if world == 1:
                     state["total"] = finish_single()
                 elif rank == 0:

@@ -121,7 +121,7 @@ static constexpr uint64_t LB_SAME_AS_NEXT = ~0ull - 1; // no newline between thi
 static constexpr uint64_t LB_OUTSIDE_SHARD = ~0ull - 2; // the line continues into a neighbouring shard
 
 // Launch one shard scan on `stream` of the device context; appends to that device's key list (no counter reset).
-int launch_scan(DevCtx &C, const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream);
+int launch_scan(DevCtx &C, const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream, int slot = 0);
 // literal kernels (scan_literal.cu)
 void launch_literal(const Plan *plan, const LitDevParams &p, int sm_count, cudaStream_t s);
 // multi kernels (scan_multi.cu)

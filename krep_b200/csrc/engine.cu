@@ -179,9 +179,11 @@ static int ctx_create(DevCtx &E, int device)
     E.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&E.scan_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&E.copy_stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&E.d_counter, 64));
-    CK(cudaMemset(E.d_counter, 0, 64));
-    E.counter_clean = true;
+    CK(cudaStreamCreateWithFlags(&E.fin_stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&E.d_counter, 64 * SCAN_SLOTS));
+    CK(cudaMemset(E.d_counter, 0, 64 * SCAN_SLOTS));
+    CK(cudaEventCreate(&E.ev_ca));
+    CK(cudaEventCreate(&E.ev_cb));
     for (int s = 0; s < SCAN_SLOTS; s++)
     {
         CK(cudaMalloc(&E.d_pack[s], (PACK_KEYS + 1) * sizeof(uint64_t)));
@@ -190,6 +192,8 @@ static int ctx_create(DevCtx &E, int device)
         CK(cudaEventCreate(&E.ev_a[s]));
         CK(cudaEventCreate(&E.ev_b[s]));
         CK(cudaEventCreateWithFlags(&E.ev_done[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&E.ev_scanned[s], cudaEventDisableTiming));
+        E.counter_clean[s] = true;
     }
     E.ready = true;
     trace("device %d: context ready (%s, %d SMs)", device, prop.name, E.sm_count);
@@ -230,8 +234,8 @@ static void ctx_destroy(DevCtx &E)
     if (!E.ready) return;
     cudaSetDevice(E.device);
     cudaDeviceSynchronize();
-    cudaFree(E.d_keys[0]);
-    cudaFree(E.d_keys[1]);
+    for (int s = 0; s < SCAN_SLOTS; s++) cudaFree(E.d_list[s]);
+    cudaFree(E.d_alt);
     cudaFree(E.d_sort_tmp);
     cudaFree(E.d_bounds);
     cudaFreeHost(E.h_bounds);
@@ -249,6 +253,7 @@ static void ctx_destroy(DevCtx &E)
         cudaEventDestroy(E.ev_a[s]);
         cudaEventDestroy(E.ev_b[s]);
         cudaEventDestroy(E.ev_done[s]);
+        cudaEventDestroy(E.ev_scanned[s]);
     }
     for (auto &s : E.stage) cudaFreeHost(s.buf);
     for (auto &s : E.stage)
@@ -256,8 +261,11 @@ static void ctx_destroy(DevCtx &E)
     for (auto ev : E.ev_pool) cudaEventDestroy(ev);
     for (auto ev : E.ring_landed) cudaEventDestroy(ev);
     for (auto ev : E.ring_scanned) cudaEventDestroy(ev);
+    cudaEventDestroy(E.ev_ca);
+    cudaEventDestroy(E.ev_cb);
     cudaStreamDestroy(E.scan_stream);
     cudaStreamDestroy(E.copy_stream);
+    cudaStreamDestroy(E.fin_stream);
     E = DevCtx();
 }
 
@@ -292,15 +300,21 @@ int ensure_keys(DevCtx &E, uint64_t cap)
     uint64_t ncap = E.key_cap ? E.key_cap : (1ull << 20);
     while (ncap < cap) ncap *= 2;
     CK(cudaDeviceSynchronize());
-    cudaFree(E.d_keys[0]);
-    cudaFree(E.d_keys[1]);
-    E.d_keys[0] = E.d_keys[1] = nullptr;
+    for (int s = 0; s < SCAN_SLOTS; s++)
+    {
+        cudaFree(E.d_list[s]);
+        E.d_list[s] = nullptr;
+    }
+    cudaFree(E.d_alt);
+    E.d_alt = nullptr;
     E.key_cap = 0;
-    CK(cudaMalloc(&E.d_keys[0], ncap * sizeof(uint64_t)));
-    CK(cudaMalloc(&E.d_keys[1], ncap * sizeof(uint64_t)));
+    for (int s = 0; s < SCAN_SLOTS; s++) CK(cudaMalloc(&E.d_list[s], ncap * sizeof(uint64_t)));
+    CK(cudaMalloc(&E.d_alt, ncap * sizeof(uint64_t)));
     E.key_cap = ncap;
     return 0;
 }
+
+unsigned long long *slot_counter(DevCtx &E, int slot) { return E.d_counter + 8 * slot; }
 
 // ---------------------------------------------------------------------------------------------
 // plan compilation
@@ -484,7 +498,7 @@ Plan *plan_build(const search_params_t *P, int algo, bool only_matching)
 // ---------------------------------------------------------------------------------------------
 // shard scan
 // ---------------------------------------------------------------------------------------------
-int launch_scan(DevCtx &E, const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream)
+int launch_scan(DevCtx &E, const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream, int slot)
 {
     if (((uintptr_t)sh->d_text & 15) != 0)
     {
@@ -510,9 +524,9 @@ int launch_scan(DevCtx &E, const Plan *plan, const krep_b200_shard_t *sh, int wa
         a.global_offset = sh->global_offset;
         a.prev_byte = sh->prev_byte;
         a.next_byte = sh->next_byte;
-        a.out = E.d_keys[0];
+        a.out = E.d_list[slot];
         a.cap = want_positions ? E.key_cap : 0;
-        a.counter = E.d_counter;
+        a.counter = slot_counter(E, slot);
         a.whole_word = plan->whole_word;
         a.want_positions = (uint32_t)want_positions;
         launch_ac(plan, pd->ac, a, E.sm_count, stream);
@@ -552,20 +566,20 @@ int launch_scan(DevCtx &E, const Plan *plan, const krep_b200_shard_t *sh, int wa
     p.mulc[2] = 1u << 8;
     p.pat_val = pd->d_pat_val;
     p.pat_mask = pd->d_pat_mask;
-    p.out = E.d_keys[0];
+    p.out = E.d_list[slot];
     p.cap = want_positions ? E.key_cap : 0;
-    p.counter = E.d_counter;
+    p.counter = slot_counter(E, slot);
     p.whole_word = plan->whole_word;
     p.want_positions = (uint32_t)want_positions;
     launch_literal(plan, p, E.sm_count, stream);
     return 0;
 }
 
-int reset_counter(DevCtx &E, cudaStream_t stream)
+int reset_counter(DevCtx &E, int slot, cudaStream_t stream)
 {
-    if (E.counter_clean) return 0;
-    CK(cudaMemsetAsync(E.d_counter, 0, 64, stream));
-    E.counter_clean = true;
+    if (E.counter_clean[slot]) return 0;
+    CK(cudaMemsetAsync(slot_counter(E, slot), 0, 64, stream));
+    E.counter_clean[slot] = true;
     return 0;
 }
 
@@ -620,6 +634,8 @@ __global__ void __launch_bounds__(1024) k_finish(unsigned long long *counter, ui
     }
 }
 
+// k_finish of the scan whose kernels were just enqueued on `stream`: it runs on the context's finish stream behind an
+// event of `stream`, so `stream` itself is free to start the next scan (other slot) while one SM sorts this list.
 int finish_scan(DevCtx &E, int slot, int want_sort, cudaStream_t stream)
 {
     static bool attr_set[MAX_DEV] = {false};
@@ -629,21 +645,23 @@ int finish_scan(DevCtx &E, int slot, int want_sort, cudaStream_t stream)
         CK(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[E.device] = true;
     }
-    k_finish<<<1, 1024, smem, stream>>>(E.d_counter, E.d_keys[0], E.key_cap, E.d_pack[slot], E.h_pack[slot],
-                                        (want_sort && E.d_keys[0]) ? 1 : 0);
+    CK(cudaEventRecord(E.ev_scanned[slot], stream));
+    CK(cudaStreamWaitEvent(E.fin_stream, E.ev_scanned[slot], 0));
+    k_finish<<<1, 1024, smem, E.fin_stream>>>(slot_counter(E, slot), E.d_list[slot], E.key_cap, E.d_pack[slot], E.h_pack[slot],
+                                              (want_sort && E.d_list[slot]) ? 1 : 0);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(E.ev_done[slot], stream));
+    CK(cudaEventRecord(E.ev_done[slot], E.fin_stream));
     count_launch();
-    E.counter_clean = true;
+    E.counter_clean[slot] = true;
     return 0;
 }
 
-// Sorts the first n keys of d_keys[0]; the sorted list ends up in *sorted (either buffer).
-int sort_keys(DevCtx &E, uint64_t n, int end_bit, cudaStream_t stream, const uint64_t **sorted)
+// Sorts the first n keys of the slot's list; the sorted list ends up in *sorted (the list or the alternate buffer).
+int sort_keys(DevCtx &E, int slot, uint64_t n, int end_bit, cudaStream_t stream, const uint64_t **sorted)
 {
-    *sorted = E.d_keys[0];
+    *sorted = E.d_list[slot];
     if (n < 2) return 0;
-    cub::DoubleBuffer<uint64_t> db(E.d_keys[0], E.d_keys[1]);
+    cub::DoubleBuffer<uint64_t> db(E.d_list[slot], E.d_alt);
     size_t need = 0;
     CK(cub::DeviceRadixSort::SortKeys(nullptr, need, db, (int64_t)n, 0, end_bit, stream));
     if (need > E.sort_tmp_bytes)
@@ -781,9 +799,11 @@ int scan_begin(DevCtx &E, const Plan *plan, const krep_b200_shard_t *sh, int wan
         set_error(-3, "krep_b200_scan_shard_begin: %d scans are already in flight on device %d", SCAN_SLOTS, E.device);
         return -3;
     }
-    if (reset_counter(E, stream) != 0) return -2;
+    // the slot's previous occupant: its k_finish (finish stream) must be done with the list and the counter
+    CK(cudaStreamWaitEvent(stream, E.ev_done[slot], 0));
+    if (reset_counter(E, slot, stream) != 0) return -2;
     CK(cudaEventRecord(E.ev_a[slot], stream));
-    int rc = launch_scan(E, plan, sh, want_positions, stream);
+    int rc = launch_scan(E, plan, sh, want_positions, stream, slot);
     if (rc != 0) return rc;
     CK(cudaEventRecord(E.ev_b[slot], stream));
     CK(cudaGetLastError());
@@ -811,8 +831,6 @@ int scan_end(DevCtx &E, int slot, ScanOut *out)
     const Plan *plan = P.plan;
     const krep_b200_shard_t *sh = &P.shard;
     cudaStream_t stream = P.stream;
-    bool later_scan = false; // a scan begun after this one is in flight: it appends to the same device list
-    for (int s2 = 0; s2 < SCAN_SLOTS; s2++) later_scan |= s2 != slot && E.pend[s2].active;
     reset_kernel_ms();
     for (int attempt = 0; attempt < 3; attempt++)
     {
@@ -828,42 +846,33 @@ int scan_end(DevCtx &E, int slot, ScanOut *out)
         out->serial = ++E.serial;
         E.result_stream = stream;
         if (!P.want_positions) return 0;
-        if (cnt <= PACK_KEYS && cnt <= E.key_cap)
-        {
-            out->stored = cnt;
-            out->d_keys = later_scan ? nullptr : E.d_keys[0]; // the device list is only intact when nothing ran behind it
-            out->h_sorted = E.h_pack[slot] + 1;
-            if (plan->count_lines && cnt)
-            {
-                if (later_scan)
-                {
-                    set_error(-3, "krep_b200_scan_shard_end: -c plans need the device list: end the scan before beginning the next");
-                    return -3;
-                }
-                return line_bounds(E, plan, sh, out->d_keys, cnt, stream, &out->d_bounds);
-            }
-            return 0;
-        }
-        if (later_scan)
-        {
-            set_error(-3, "krep_b200_scan_shard_end: %llu occurrences do not fit the packed read-back (%u) and another scan is "
-                          "already in flight behind this one: end each scan before beginning the next for lists this long",
-                      (unsigned long long)cnt, PACK_KEYS);
-            return -3;
-        }
         if (cnt <= E.key_cap)
         {
+            int rc = 0;
             out->stored = cnt;
-            int rc = sort_keys(E, cnt, key_end_bit(plan, sh->global_offset + sh->avail_len), stream, &out->d_keys);
+            if (cnt <= PACK_KEYS)
+            {
+                out->d_keys = E.d_list[slot];
+                out->h_sorted = E.h_pack[slot] + 1;
+            }
+            else
+                rc = sort_keys(E, slot, cnt, key_end_bit(plan, sh->global_offset + sh->avail_len), stream, &out->d_keys);
             if (rc == 0 && plan->count_lines) rc = line_bounds(E, plan, sh, out->d_keys, cnt, stream, &out->d_bounds);
             return rc;
         }
         // the list overflowed (the counter stays exact past capacity): grow it and scan again
         out->overflow = 1;
+        for (int s2 = 0; s2 < SCAN_SLOTS; s2++)
+            if (s2 != slot && E.pend[s2].active)
+            {
+                set_error(-3, "krep_b200_scan_shard_end: the occurrence list overflowed while another scan is in flight; end each "
+                              "scan before beginning the next until the list has grown");
+                return -3;
+            }
         if (ensure_keys(E, cnt + cnt / 8 + 1024) != 0) return -2;
-        if (reset_counter(E, stream) != 0) return -2;
+        if (reset_counter(E, slot, stream) != 0) return -2;
         CK(cudaEventRecord(E.ev_a[slot], stream));
-        int rc = launch_scan(E, plan, sh, 1, stream);
+        int rc = launch_scan(E, plan, sh, 1, stream, slot);
         if (rc != 0) return rc;
         CK(cudaEventRecord(E.ev_b[slot], stream));
         if (finish_scan(E, slot, 1, stream) != 0) return -2;
@@ -1171,6 +1180,7 @@ int krep_b200_export_packed_async(int ticket, void *d_dst, uint64_t max_keys)
         return -3;
     }
     cudaStream_t s = C->pend[slot].stream;
+    CK(cudaStreamWaitEvent(s, C->ev_done[slot], 0)); // the finish kernel runs on its own stream
     CK(cudaMemcpyAsync(d_dst, C->d_pack[slot], (max_keys + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
     return 0;
 }

@@ -37,9 +37,12 @@ struct DevCtx
     bool ready = false;
     int device = 0, sm_count = 0;
     cudaStream_t scan_stream = nullptr, copy_stream = nullptr;
-    unsigned long long *d_counter = nullptr;
-    bool counter_clean = false; // k_finish leaves the counter at zero: the next scan needs no memset
-    uint64_t *d_keys[2] = {nullptr, nullptr};
+    cudaStream_t fin_stream = nullptr; // k_finish runs here, behind its scan, so that the NEXT scan (other slot) overlaps it
+    // every scan slot has its own occurrence list and counter: scan i+1 may append while k_finish still sorts list i
+    unsigned long long *d_counter = nullptr;                // SCAN_SLOTS counters, 64 bytes apart
+    bool counter_clean[SCAN_SLOTS] = {false, false};        // k_finish leaves the counter at zero: no memset before the next scan
+    uint64_t *d_list[SCAN_SLOTS] = {nullptr, nullptr};      // key_cap keys each
+    uint64_t *d_alt = nullptr;                              // radix sort's alternate buffer (lists beyond PACK_KEYS)
     uint64_t key_cap = 0;
     void *d_sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
@@ -52,6 +55,8 @@ struct DevCtx
     uint64_t *d_pack[SCAN_SLOTS] = {nullptr, nullptr}, *h_pack[SCAN_SLOTS] = {nullptr, nullptr};
     cudaEvent_t ev_a[SCAN_SLOTS] = {nullptr, nullptr}, ev_b[SCAN_SLOTS] = {nullptr, nullptr};
     cudaEvent_t ev_done[SCAN_SLOTS] = {nullptr, nullptr}; // recorded after k_finish: what scan_end waits for
+    cudaEvent_t ev_scanned[SCAN_SLOTS] = {nullptr, nullptr}; // recorded on the scan's stream when its kernels are enqueued
+    cudaEvent_t ev_ca = nullptr, ev_cb = nullptr;          // timing of krep_b200_count_lines_shard
     PendingScan pend[SCAN_SLOTS];
     int next_slot = 0;
     uint64_t serial = 0;
@@ -105,13 +110,14 @@ void plan_free(Plan *p);
 const PlanDev *plan_on_device(const Plan *p, DevCtx &C); // uploads on first use; nullptr on CUDA errors
 int resolve_algo(const search_params_t *P, int algo); // host_api.cu: precondition fallbacks of the simd_* entries
 
+unsigned long long *slot_counter(DevCtx &C, int slot);
 int scan_begin(DevCtx &C, const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream, int *slot);
 int scan_end(DevCtx &C, int slot, ScanOut *out);
 int scan_shard(DevCtx &C, const Plan *plan, const krep_b200_shard_t *sh, int want_positions, cudaStream_t stream, ScanOut *out);
 int finish_scan(DevCtx &C, int slot, int want_sort, cudaStream_t stream); // k_finish: count + small-list sort + counter reset
 int ensure_keys(DevCtx &C, uint64_t cap);
-int reset_counter(DevCtx &C, cudaStream_t stream);
-int sort_keys(DevCtx &C, uint64_t n, int end_bit, cudaStream_t stream, const uint64_t **sorted);
+int reset_counter(DevCtx &C, int slot, cudaStream_t stream);
+int sort_keys(DevCtx &C, int slot, uint64_t n, int end_bit, cudaStream_t stream, const uint64_t **sorted);
 int key_end_bit(const Plan *plan, uint64_t max_offset);
 int fetch_keys(DevCtx &C, const ScanOut &so, const uint64_t **h); // sorted keys on the host (no copy when they came back packed)
 void add_kernel_ms(float ms);

@@ -286,7 +286,8 @@ static int stream_range(RangeJob &J)
     const int slot = 0;
     for (int attempt = 0; attempt < 3; attempt++)
     {
-        if (reset_counter(E, E.scan_stream) != 0) return -2;
+        CKH(cudaStreamWaitEvent(E.scan_stream, E.ev_done[slot], 0));
+        if (reset_counter(E, slot, E.scan_stream) != 0) return -2;
         for (size_t c = 0; c < nchunks; c++)
         {
             const size_t off = J.begin + c * chunk, len = std::min(chunk, J.end - off);
@@ -318,7 +319,7 @@ static int stream_range(RangeJob &J)
             cudaEvent_t a = pool_event(E, 2 * c), b = pool_event(E, 2 * c + 1);
             CKH(cudaEventRecord(a, E.scan_stream));
             int rc = J.count_lines ? launch_count_lines(E, plan, &part, E.scan_stream, c)
-                                   : launch_scan(E, plan, &part, J.want_positions, E.scan_stream);
+                                   : launch_scan(E, plan, &part, J.want_positions, E.scan_stream, slot);
             if (rc != 0) return rc;
             CKH(cudaEventRecord(b, E.scan_stream));
             CKH(cudaEventRecord(E.ring_scanned[rs], E.scan_stream));
@@ -326,6 +327,7 @@ static int stream_range(RangeJob &J)
         CKH(cudaGetLastError());
         if (!J.count_lines && finish_scan(E, slot, J.want_positions, E.scan_stream) != 0) return -2;
         CKH(cudaStreamSynchronize(E.scan_stream));
+        if (!J.count_lines) CKH(cudaEventSynchronize(E.ev_done[slot])); // k_finish runs on the finish stream
         for (auto &s : E.stage) s.in_flight = false;
         for (size_t c = 0; c < nchunks; c++)
         {
@@ -351,11 +353,11 @@ static int stream_range(RangeJob &J)
             J.so.stored = cnt;
             if (cnt <= PACK_KEYS)
             {
-                J.so.d_keys = E.d_keys[0];
+                J.so.d_keys = E.d_list[slot];
                 J.so.h_sorted = E.h_pack[slot] + 1;
                 return 0;
             }
-            return sort_keys(E, cnt, key_end_bit(plan, n), E.scan_stream, &J.so.d_keys);
+            return sort_keys(E, slot, cnt, key_end_bit(plan, n), E.scan_stream, &J.so.d_keys);
         }
         // list overflowed: grow it and stage the range again (the ring holds only the last chunks)
         J.so.overflow = 1;
@@ -1074,16 +1076,16 @@ int krep_b200_count_lines_shard(const krep_b200_plan_t *plan_, const search_para
     if (!C) return -1;
     cudaStream_t st = stream ? (cudaStream_t)stream : C->scan_stream;
     reset_kernel_ms();
-    if (cudaEventRecord(C->ev_a[0], st) != cudaSuccess) return -2;
+    if (cudaEventRecord(C->ev_ca, st) != cudaSuccess) return -2;
     int rc = launch_count_lines(*C, plan, shard, st, 0);
     if (rc != 0) return rc;
-    if (cudaEventRecord(C->ev_b[0], st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    if (cudaEventRecord(C->ev_cb, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
     {
         set_error(-2, "CUDA error in the fused line count (%s)", cudaGetErrorString(cudaGetLastError()));
         return -2;
     }
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, C->ev_a[0], C->ev_b[0]);
+    cudaEventElapsedTime(&ms, C->ev_ca, C->ev_cb);
     add_kernel_ms(ms);
     out->lines = C->h_line_out[0];
     out->flags = (uint32_t)C->h_line_out[1];

@@ -229,8 +229,14 @@ __device__ __noinline__ unsigned slow_window4(const LitDevParams &p, uint64_t gr
 // Main loads of the window kernel: the sector that holds a warp's "next word" is touched twice (once as lane 31's
 // next-word load, once as the following warp's vector), so these loads keep the default L2 policy instead of
 // evict-first; KREP_B200_W4_CS=1 at build time restores the streaming hint for comparison.
+// Measured on the B200 (profiles/r2c_window4_variants.md, -i 4-byte literal, 10 GiB): the window kernel is bound by its
+// integer pipe, so everything added to its streaming loop costs: every lane loading its own next word (0) 1.798 ms;
+// lane 31 loading + shuffle (2) 1.858 ms; warp-cooperative emission on top of either 2.25-2.27 ms.  Defaults: 0 / 0.
 #ifndef KREP_B200_W4_NX
-#define KREP_B200_W4_NX 2 // how the window kernel gets the word behind a vector: 0 = every lane loads it, 1 / 2 = shuffle
+#define KREP_B200_W4_NX 0 // how the window kernel gets the word behind a vector: 0 = every lane loads it, 1 / 2 = shuffle
+#endif
+#ifndef KREP_B200_W4_WARP_EMIT
+#define KREP_B200_W4_WARP_EMIT 0
 #endif
 #ifdef KREP_B200_W4_CS
 #define WLOAD(q) ld_stream(q)
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ 
 #pragma unroll
         for (int u = 0; u < UNROLL; u++)
             hm |= hit_vec_w<FOLD, MASKED>(v[u], nx[u], fold, mask, k0, c1, c2, c3) ? (1u << u) : 0u;
-#if KREP_B200_WARP_EMIT
+#if KREP_B200_W4_WARP_EMIT
         const uint32_t anyhm = __reduce_or_sync(0xffffffffu, hm);
         if (anyhm)
         {

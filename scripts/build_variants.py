@@ -10,11 +10,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from krep_b200 import build as kb  # noqa: E402
 
-VARIANTS = {
-    "nx0": ["-DKREP_B200_W4_NX=0"],
-    "nx1": ["-DKREP_B200_W4_NX=1"],
-    "nx0_lane_emit": ["-DKREP_B200_W4_NX=0", "-DKREP_B200_WARP_EMIT=0"],
-    "nx2_lane_emit": ["-DKREP_B200_W4_NX=2", "-DKREP_B200_WARP_EMIT=0"],
+VARIANTS = {   # default build: W4_NX=0, W4_WARP_EMIT=0, WARP_EMIT=1 (aligned-word kernel only)
+    "nx2": ["-DKREP_B200_W4_NX=2"],
+    "nx0_warp_emit": ["-DKREP_B200_W4_WARP_EMIT=1"],
+    "nx2_warp_emit": ["-DKREP_B200_W4_NX=2", "-DKREP_B200_W4_WARP_EMIT=1"],
+    "aligned_lane_emit": ["-DKREP_B200_WARP_EMIT=0"],
 }
 
 
