@@ -584,73 +584,76 @@ int reset_counter(DevCtx &E, int slot, cudaStream_t stream)
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_finish — the tail of every scan, one CTA: publishes the occurrence count, zeroes the counter for the next scan, and
-// when the list is short (<= PACK_KEYS, the normal case on low-hit-rate corpora: 10 240 occurrences in the 10 GiB
-// benchmark shard) sorts it in shared memory (bitonic, 64-bit keys) and writes it three ways: back in place (the device
-// list later stages read), into d_pack (what a multi-GPU host hands to its gather) and through mapped pinned memory
-// into h_pack, so that count AND sorted occurrences reach the host with the ONE stream synchronisation the scan needs
-// anyway — no CUB launches, no second read-back.
+// k_finish — the tail of every scan: publishes the occurrence count, and when the list is short (<= PACK_KEYS, the
+// normal case on low-hit-rate corpora: 10 240 occurrences in the 10 GiB benchmark shard) sorts it into d_pack (the
+// device copy later stages and a multi-GPU host's gather read), from where it goes to the host's pinned
+// memory — one fixed-size copy of the packed row behind the kernel — so that count AND sorted occurrences reach the host
+// with the one synchronisation the scan needs anyway: no CUB launches, no second read-back.
+//
+// The sort is a RANK sort spread over 128 CTAs: thread t of CTA b owns key b*128+t, streams the whole list through
+// shared memory in 2048-key pieces (every thread reads the same word: a broadcast, no bank conflicts) and counts the
+// keys that order before its own; that count is the key's final position.  n^2 compares — 10^8 for 10 240 keys, about
+// 25 us on the whole GPU — instead of the 105 barrier-separated passes of a one-CTA bitonic network (165 us measured,
+// profiles/r2c_literal8_launches.csv): with ~10^4 keys the quadratic algorithm is the one that uses the machine.
+// The last CTA to finish zeroes the scan counter and the done-counter for the slot's next scan.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_finish(unsigned long long *counter, uint64_t *keys, uint64_t cap, uint64_t *d_pack,
-                                                 uint64_t *h_pack, int want_sort)
+static constexpr int FIN_THREADS = 128, FIN_PIECE = 2048;
+
+__global__ void __launch_bounds__(FIN_THREADS) k_finish(unsigned long long *counter, const uint64_t *__restrict__ keys, uint64_t cap,
+                                                        uint64_t *d_pack, int want_sort)
 {
-    extern __shared__ __align__(16) uint64_t s_keys[];
-    const unsigned long long cnt = *counter;
-    __syncthreads(); // every thread has read the count before it is reset
-    if (threadIdx.x == 0)
-    {
-        *counter = 0;
-        d_pack[0] = cnt;
-        h_pack[0] = cnt;
-    }
-    if (!want_sort || cnt == 0 || cnt > PACK_KEYS || cnt > cap) return;
-    const uint32_t n = (uint32_t)cnt;
-    uint32_t N = 2;
-    while (N < n) N <<= 1;
-    for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) s_keys[i] = i < n ? keys[i] : ~0ull;
+    __shared__ uint64_t s_keys[FIN_PIECE];
+    __shared__ unsigned long long s_cnt;
+    if (threadIdx.x == 0) s_cnt = counter[0];
     __syncthreads();
-    for (uint32_t k = 2; k <= N; k <<= 1)
-        for (uint32_t j = k >> 1; j > 0; j >>= 1)
+    const unsigned long long cnt = s_cnt;
+    if (blockIdx.x == 0 && threadIdx.x == 0) d_pack[0] = cnt;
+    const bool sorting = want_sort && cnt != 0 && cnt <= PACK_KEYS && cnt <= cap;
+    const uint32_t n = sorting ? (uint32_t)cnt : 0u;
+    const uint32_t idx = blockIdx.x * FIN_THREADS + threadIdx.x;
+    if (blockIdx.x * FIN_THREADS < n) // this CTA owns at least one key
+    {
+        const uint64_t mine = idx < n ? keys[idx] : ~0ull;
+        uint32_t rank = 0;
+        for (uint32_t base = 0; base < n; base += FIN_PIECE)
         {
-            for (uint32_t t = threadIdx.x; t < N / 2; t += blockDim.x)
-            {
-                const uint32_t i = 2 * t - (t & (j - 1)); // lower element of pair t at distance j
-                const uint64_t a = s_keys[i], b = s_keys[i + j];
-                const bool up = (i & k) == 0;
-                if ((a > b) == up)
-                {
-                    s_keys[i] = b;
-                    s_keys[i + j] = a;
-                }
-            }
+            const uint32_t m = n - base < FIN_PIECE ? n - base : FIN_PIECE;
+            for (uint32_t j = threadIdx.x; j < FIN_PIECE; j += FIN_THREADS) s_keys[j] = j < m ? keys[base + j] : ~0ull;
+            __syncthreads();
+            // keys are distinct (an occurrence key is unique), so "<" alone is a total order; padding (~0) never counts
+            const uint32_t mr = (m + 7u) & ~7u;
+#pragma unroll 8
+            for (uint32_t j = 0; j < mr; j++) rank += s_keys[j] < mine ? 1u : 0u;
             __syncthreads();
         }
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        if (idx < n) d_pack[1 + rank] = mine;
+    }
+    // the last CTA out resets the counters (counter[1] counts finished CTAs)
+    __syncthreads();
+    if (threadIdx.x == 0)
     {
-        const uint64_t v = s_keys[i];
-        keys[i] = v;
-        d_pack[1 + i] = v;
-        h_pack[1 + i] = v;
+        __threadfence();
+        const unsigned long long done = atomicAdd(&counter[1], 1ULL);
+        if (done == gridDim.x - 1)
+        {
+            counter[0] = 0;
+            counter[1] = 0;
+        }
     }
 }
 
-// k_finish of the scan whose kernels were just enqueued on `stream`: it runs on the context's finish stream behind an
-// event of `stream`, so `stream` itself is free to start the next scan (other slot) while one SM sorts this list.
+// k_finish of the scan whose kernels were just enqueued on `stream`, on the same stream: at ~25 us it is cheaper to run it
+// between two scans than beside one (a CTA that needs registers on an SM the scan's persistent CTAs already fill only
+// gets there when they exit — measured in run r2d: the overlapped version serialised anyway and slowed the scan's tail).
 int finish_scan(DevCtx &E, int slot, int want_sort, cudaStream_t stream)
 {
-    static bool attr_set[MAX_DEV] = {false};
-    const size_t smem = (size_t)PACK_KEYS * sizeof(uint64_t);
-    if (!attr_set[E.device])
-    {
-        CK(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[E.device] = true;
-    }
-    CK(cudaEventRecord(E.ev_scanned[slot], stream));
-    CK(cudaStreamWaitEvent(E.fin_stream, E.ev_scanned[slot], 0));
-    k_finish<<<1, 1024, smem, E.fin_stream>>>(slot_counter(E, slot), E.d_list[slot], E.key_cap, E.d_pack[slot], E.h_pack[slot],
-                                              (want_sort && E.d_list[slot]) ? 1 : 0);
+    k_finish<<<PACK_KEYS / FIN_THREADS, FIN_THREADS, 0, stream>>>(slot_counter(E, slot), E.d_list[slot], E.key_cap, E.d_pack[slot],
+                                                                 (want_sort && E.d_list[slot]) ? 1 : 0);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(E.ev_done[slot], E.fin_stream));
+    // count + (possibly) sorted keys to the host in one DMA of the whole packed row: 128 KiB over PCIe is ~5 us, cheaper than
+    // having the sort's scattered 8-byte stores go through mapped memory
+    CK(cudaMemcpyAsync(E.h_pack[slot], E.d_pack[slot], (want_sort ? PACK_KEYS + 1 : 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaEventRecord(E.ev_done[slot], stream));
     count_launch();
     E.counter_clean[slot] = true;
     return 0;
@@ -852,7 +855,7 @@ int scan_end(DevCtx &E, int slot, ScanOut *out)
             out->stored = cnt;
             if (cnt <= PACK_KEYS)
             {
-                out->d_keys = E.d_list[slot];
+                out->d_keys = E.d_pack[slot] + 1; // the rank sort writes the ordered list here (the slot's list stays raw)
                 out->h_sorted = E.h_pack[slot] + 1;
             }
             else

@@ -37,9 +37,9 @@ struct DevCtx
     bool ready = false;
     int device = 0, sm_count = 0;
     cudaStream_t scan_stream = nullptr, copy_stream = nullptr;
-    cudaStream_t fin_stream = nullptr; // k_finish runs here, behind its scan, so that the NEXT scan (other slot) overlaps it
+    cudaStream_t fin_stream = nullptr; // spare stream (k_finish ran here in an experiment; it now follows its scan in-stream)
     // every scan slot has its own occurrence list and counter: scan i+1 may append while k_finish still sorts list i
-    unsigned long long *d_counter = nullptr;                // SCAN_SLOTS counters, 64 bytes apart
+    unsigned long long *d_counter = nullptr;                // per slot, 64 bytes apart: [0] occurrences, [1] finished k_finish CTAs
     bool counter_clean[SCAN_SLOTS] = {false, false};        // k_finish leaves the counter at zero: no memset before the next scan
     uint64_t *d_list[SCAN_SLOTS] = {nullptr, nullptr};      // key_cap keys each
     uint64_t *d_alt = nullptr;                              // radix sort's alternate buffer (lists beyond PACK_KEYS)

@@ -353,7 +353,7 @@ static int stream_range(RangeJob &J)
             J.so.stored = cnt;
             if (cnt <= PACK_KEYS)
             {
-                J.so.d_keys = E.d_list[slot];
+                J.so.d_keys = E.d_pack[slot] + 1;
                 J.so.h_sorted = E.h_pack[slot] + 1;
                 return 0;
             }

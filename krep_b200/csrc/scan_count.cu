@@ -63,6 +63,8 @@ struct PartState
     uint64_t covered_to = 0; // newline knowledge is complete for bytes below this
 };
 
+__device__ __noinline__ unsigned verify_exact_call(const LitDevParams &p, long long cand) { return verify_exact(p, cand); }
+
 // 4-bit mask of the bytes of w that equal '\n' (exact per byte)
 __device__ __forceinline__ uint32_t nl_nibble(uint32_t w)
 {
@@ -185,79 +187,49 @@ __device__ __forceinline__ void account(PartState &S, uint32_t hm, uint32_t nm)
     }
 }
 
-// One 512-byte vector with at least one filter candidate.  `nlmask4` bit u' = vector u' of the current tile (which
-// starts at tile_lo) holds a newline — from the registers, valid when the whole tile lies inside the partition's newline
-// range (tile_inside); it settles "did the open line end in the skipped vectors of this tile" without touching memory.
+// Exact hit mask of this lane's 16 bytes (bit = position of the hit's proxy byte inside the unit).
 template <bool WINDOW>
-__device__ __noinline__ void count_vector(const CountDev &D, PartState &S, uint64_t vec_lo, bool valid, uint4 v, uint32_t nx,
-                                          uint64_t nl_lo, uint64_t nl_hi, uint64_t tile_lo, uint32_t nlmask4, bool tile_inside)
+__device__ __forceinline__ uint32_t hit_mask16(const CountDev &D, uint64_t unit, const uint4 &v, uint32_t nx)
 {
     const LitDevParams &p = D.p;
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w[5] = {v.x, v.y, v.z, v.w, nx};
+    uint32_t hm = 0;
+    if (WINDOW)
     {
-        const uint64_t upto = vec_lo > nl_lo ? vec_lo : nl_lo;
-        if (S.covered_to < upto && (S.pending || (!S.has_hit && !S.seen_nl)))
-        {
-            bool found = false;
-            if (tile_inside)
+        const uint32_t mask = p.fold & p.win_mask, k0 = p.K[0];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
             {
-#pragma unroll
-                for (int u2 = 0; u2 < 4; u2++)
-                    found |= ((nlmask4 >> u2) & 1u) && tile_lo + 512ull * u2 >= S.covered_to && tile_lo + 512ull * u2 < vec_lo;
-                if (!found && S.covered_to < tile_lo) found = scan_for_newline(p, S.covered_to, tile_lo);
-            }
-            else
-                found = scan_for_newline(p, S.covered_to, upto);
-            if (found)
-            {
-                S.pending = false;
-                S.seen_nl = true;
-            }
-        }
-    }
-    const uint64_t unit = vec_lo + 16ull * lane;
-    uint32_t hm = 0, nm = 0;
-    if (valid)
-    {
-        const uint32_t w[5] = {v.x, v.y, v.z, v.w, nx};
-        if (WINDOW)
-        {
-            const uint32_t mask = p.fold & p.win_mask, k0 = p.K[0];
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-#pragma unroll
-                for (int r = 0; r < 4; r++)
+                const uint32_t win = r == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * r);
+                if ((win & mask) == k0)
                 {
-                    const uint32_t win = r == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * r);
-                    if ((win & mask) == k0)
-                    {
-                        const uint64_t st = unit + 4 * k + r;
-                        const bool ok = D.exact ? (st >= p.own_begin && st < p.own_end && st + p.m <= p.avail_len)
-                                                : verify_exact(p, (long long)st) != 0;
-                        if (ok) hm |= 1u << (4 * k + r);
-                    }
+                    const uint64_t st = unit + 4 * k + r;
+                    const bool ok = D.exact ? (st >= p.own_begin && st < p.own_end && st + p.m <= p.avail_len)
+                                            : verify_exact_call(p, (long long)st) != 0;
+                    if (ok) hm |= 1u << (4 * k + r);
                 }
-        }
-        else
-        {
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-#pragma unroll
-                for (int d = 0; d < 4; d++)
-                    if ((w[k] & p.fold) == p.K[d] && verify_exact(p, (long long)(unit + 4 * k) - d)) hm |= 1u << (4 * k);
-        }
-        nm = nl_mask16(v) & range_mask16(unit, nl_lo, nl_hi);
+            }
     }
-    account(S, hm, nm);
-    S.covered_to = vec_lo + 512;
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int d = 0; d < 4; d++)
+                if ((w[k] & p.fold) == p.K[d] && verify_exact_call(p, (long long)(unit + 4 * k) - d)) hm |= 1u << (4 * k);
+    }
+    return hm;
 }
 
 // Bytes behind the last full vector of the shard: one byte per lane.
-__device__ __noinline__ void count_tail(const CountDev &D, PartState &S, uint64_t cov, uint64_t nl_lo, uint64_t nl_hi, bool window)
+// (state by value in, by value out: a reference would pin the caller's state to local memory for the whole kernel)
+__device__ __noinline__ PartState count_tail(const CountDev &D, PartState S, uint64_t cov, uint64_t nl_lo, uint64_t nl_hi, bool window)
 {
     const LitDevParams &p = D.p;
     const uint32_t lane = threadIdx.x & 31;
-    if (p.avail_len < p.emit_len && cov >= nl_hi) return;
+    if (p.avail_len < p.emit_len && cov >= nl_hi) return S;
     const uint64_t last_start = p.avail_len >= p.emit_len ? p.avail_len - p.emit_len : 0;
     uint64_t end = nl_hi > last_start + 1 ? nl_hi : last_start + 1;
     if (!window && end < cov + 1) end = cov + 1; // starts in [cov - 3, cov) are picked up by the lane at cov
@@ -279,10 +251,14 @@ __device__ __noinline__ void count_tail(const CountDev &D, PartState &S, uint64_
         account(S, hm, nm);
         S.covered_to = base + 32;
     }
+    return S;
 }
 
+#ifndef KREP_B200_COUNT_MINB
+#define KREP_B200_COUNT_MINB 3 // resident CTAs per SM the kernel is compiled for (3: 80 registers; 2: 128, no spills)
+#endif
 template <bool WINDOW, bool FOLD, bool MASKED>
-__global__ void __launch_bounds__(256, 3) k_count_lines(const __grid_constant__ CountDev D)
+__global__ void __launch_bounds__(256, KREP_B200_COUNT_MINB) k_count_lines(const __grid_constant__ CountDev D)
 {
     const LitDevParams &p = D.p;
     const uint4 *__restrict__ t4 = reinterpret_cast<const uint4 *>(p.text);
@@ -333,23 +309,29 @@ __global__ void __launch_bounds__(256, 3) k_count_lines(const __grid_constant__ 
             const uint32_t any = __reduce_or_sync(0xffffffffu, cand);
             if (any)
             {
+                // A tile with a candidate is accounted as a whole, in place: hit masks for the vectors that have candidates,
+                // newline masks for all four (from the registers), one round of ballots per vector.  Only the gap between the
+                // previous accounted tile and this one may need memory (settle), and only while a line is open.
                 const uint64_t tile_lo = g * 16;
-                const bool tile_inside = tile_lo >= nl_lo && tile_lo + 2048 <= nl_hi && g + 128 <= gb;
-                uint32_t nlmask4 = 0;
-                if (tile_inside)
-                {
-                    uint32_t mine = 0;
-#pragma unroll
-                    for (int u = 0; u < 4; u++) mine |= nl_mask16(v[u]) ? (1u << u) : 0u;
-                    nlmask4 = __reduce_or_sync(0xffffffffu, mine);
-                }
+                settle(p, S, tile_lo > nl_lo ? tile_lo : nl_lo);
+                const bool inside = tile_lo >= nl_lo && tile_lo + 2048 <= nl_hi;
 #pragma unroll
                 for (int u = 0; u < 4; u++)
-                    if ((any >> u) & 1u)
-                        count_vector<WINDOW>(D, S, (g + 32 * u) * 16, ok[u], v[u], nx[u], nl_lo, nl_hi, tile_lo, nlmask4, tile_inside);
+                {
+                    const uint64_t unit = tile_lo + 512ull * u + 16ull * lane;
+                    uint32_t hm = 0, nm = 0;
+                    if (ok[u])
+                    {
+                        if ((cand >> u) & 1u) hm = hit_mask16<WINDOW>(D, unit, v[u], nx[u]);
+                        nm = nl_mask16(v[u]);
+                        if (!inside) nm &= range_mask16(unit, nl_lo, nl_hi);
+                    }
+                    account(S, hm, nm);
+                }
+                S.covered_to = tile_lo + 2048;
             }
         }
-        if (last_part && D.tail) count_tail(D, S, gb * 16, nl_lo, nl_hi, WINDOW);
+        if (last_part && D.tail) S = count_tail(D, S, gb * 16, nl_lo, nl_hi, WINDOW);
         // close the partition
         uint32_t flags = 0;
         if (S.has_hit)
@@ -540,7 +522,7 @@ int launch_count_lines(DevCtx &E, const Plan *plan, const krep_b200_shard_t *sh,
     D.recs = (LineRec *)E.d_line_recs;
     const bool folded = plan->fold != 0xFFFFFFFFu, masked = plan->win_mask != 0xFFFFFFFFu;
     const uint64_t want_blocks = ((uint64_t)D.n_parts + 7) / 8;
-    const unsigned grid = (unsigned)std::min<uint64_t>(want_blocks, (uint64_t)E.sm_count * 3);
+    const unsigned grid = (unsigned)std::min<uint64_t>(want_blocks, (uint64_t)E.sm_count * KREP_B200_COUNT_MINB);
     if (!window)
     {
         if (folded) k_count_lines<false, true, false><<<grid, 256, 0, stream>>>(D);

@@ -292,23 +292,27 @@ __global__ void __launch_bounds__(256, 4) k_lit_window4(const __grid_constant__ 
 #pragma unroll
         for (int u = 0; u < UNROLL; u++)
             hm |= hit_vec_w<FOLD, MASKED>(v[u], nx[u], fold, mask, k0, c1, c2, c3) ? (1u << u) : 0u;
-#if KREP_B200_W4_WARP_EMIT
-        const uint32_t anyhm = __reduce_or_sync(0xffffffffu, hm);
-        if (anyhm)
+        // Needles of 1..3 bytes (MASKED) occur often — `the` once per 7 KiB of English-like text, once per 64 B in the density
+        // sweep — so their kernels emit warp-cooperatively (one atomicAdd per warp and vector: 5x faster at one occurrence
+        // per KiB, run r2d); the 4..6-byte kernels keep the per-occurrence path, whose streaming loop is 25 % shorter
+        // (profiles/r2c_window4_variants.md).
+        if constexpr (MASKED || KREP_B200_W4_WARP_EMIT)
         {
+            const uint32_t anyhm = __reduce_or_sync(0xffffffffu, hm);
+            if (anyhm)
+            {
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++)
-                if ((anyhm >> u) & 1u)
-                    local_cnt += emit_warp<true>(p, g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u], nx[u], (hm >> u) & 1u);
+                for (int u = 0; u < UNROLL; u++)
+                    if ((anyhm >> u) & 1u)
+                        local_cnt += emit_warp<true>(p, g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u], nx[u], (hm >> u) & 1u);
+            }
         }
-#else
-        if (hm)
+        else if (hm)
         {
 #pragma unroll
             for (int u = 0; u < UNROLL; u++)
                 if ((hm >> u) & 1u) local_cnt += slow_window4(p, g0 + (uint64_t)u * blockDim.x + threadIdx.x, v[u], nx[u]);
         }
-#endif
     }
     if (g0 < p.group_end)
     {

@@ -15,6 +15,7 @@ VARIANTS = {   # default build: W4_NX=0, W4_WARP_EMIT=0, WARP_EMIT=1 (aligned-wo
     "nx0_warp_emit": ["-DKREP_B200_W4_WARP_EMIT=1"],
     "nx2_warp_emit": ["-DKREP_B200_W4_NX=2", "-DKREP_B200_W4_WARP_EMIT=1"],
     "aligned_lane_emit": ["-DKREP_B200_WARP_EMIT=0"],
+    "count_minb2": ["scan_count.cu", "-DKREP_B200_COUNT_MINB=2"],
 }
 
 
@@ -23,10 +24,13 @@ def main():
     out_dir = os.path.join(ROOT, "build", "variants")
     os.makedirs(out_dir, exist_ok=True)
     objdir = os.path.join(kb.HERE, "build")
-    others = [os.path.join(objdir, s.rsplit(".", 1)[0] + ".o") for s in kb.SOURCES if s != "scan_literal.cu"]
     for name, flags in VARIANTS.items():
-        obj = os.path.join(out_dir, f"scan_literal_{name}.o")
-        subprocess.run([kb.NVCC, *[f for f in kb.FLAGS if f not in ("-Xptxas", "-v")], *flags, "-c", os.path.join(kb.CSRC, "scan_literal.cu"), "-o", obj], check=True)
+        src = "scan_literal.cu"
+        if flags and flags[0].endswith(".cu"):
+            src, flags = flags[0], flags[1:]
+        others = [os.path.join(objdir, s.rsplit(".", 1)[0] + ".o") for s in kb.SOURCES if s != src]
+        obj = os.path.join(out_dir, f"{src[:-3]}_{name}.o")
+        subprocess.run([kb.NVCC, *[f for f in kb.FLAGS if f not in ("-Xptxas", "-v")], *flags, "-c", os.path.join(kb.CSRC, src), "-o", obj], check=True)
         so = os.path.join(out_dir, f"libkrep_b200_{name}.so")
         subprocess.run([kb.NVCC, "-shared", "-o", so, obj, *others, "-Xcompiler", "-fopenmp", "-lgomp"], check=True)
         print(so)
