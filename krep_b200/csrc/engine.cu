@@ -590,14 +590,15 @@ int reset_counter(DevCtx &E, int slot, cudaStream_t stream)
 // memory — one fixed-size copy of the packed row behind the kernel — so that count AND sorted occurrences reach the host
 // with the one synchronisation the scan needs anyway: no CUB launches, no second read-back.
 //
-// The sort is a RANK sort spread over 128 CTAs: thread t of CTA b owns key b*128+t, streams the whole list through
-// shared memory in 2048-key pieces (every thread reads the same word: a broadcast, no bank conflicts) and counts the
-// keys that order before its own; that count is the key's final position.  n^2 compares — 10^8 for 10 240 keys, about
-// 25 us on the whole GPU — instead of the 105 barrier-separated passes of a one-CTA bitonic network (165 us measured,
-// profiles/r2c_literal8_launches.csv): with ~10^4 keys the quadratic algorithm is the one that uses the machine.
+// The sort is a RANK sort spread over the GPU: a CTA owns 64 keys, streams the whole list through shared memory in
+// 2048-key pieces and counts, for each of its keys, the keys that order before it (8 lanes per key, each taking every
+// 8th list entry; lanes of one slice read the same word — a broadcast); that count is the key's final position.  n^2
+// compares, 10^8 for 10 240 keys, on 160 CTAs x 16 warps — instead of the 105 barrier-separated passes of a one-CTA
+// bitonic network (165 us measured, profiles/r2c_literal8_launches.csv; one thread per key without the 8-way split:
+// 86 us, r2e): with ~10^4 keys the quadratic algorithm is the one that uses the machine.
 // The last CTA to finish zeroes the scan counter and the done-counter for the slot's next scan.
 // ---------------------------------------------------------------------------------------------
-static constexpr int FIN_THREADS = 128, FIN_PIECE = 2048;
+static constexpr int FIN_THREADS = 512, FIN_SLICES = 8, FIN_KEYS = FIN_THREADS / FIN_SLICES, FIN_PIECE = 2048;
 
 __global__ void __launch_bounds__(FIN_THREADS) k_finish(unsigned long long *counter, const uint64_t *__restrict__ keys, uint64_t cap,
                                                         uint64_t *d_pack, int want_sort)
@@ -610,8 +611,10 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(unsigned long long *coun
     if (blockIdx.x == 0 && threadIdx.x == 0) d_pack[0] = cnt;
     const bool sorting = want_sort && cnt != 0 && cnt <= PACK_KEYS && cnt <= cap;
     const uint32_t n = sorting ? (uint32_t)cnt : 0u;
-    const uint32_t idx = blockIdx.x * FIN_THREADS + threadIdx.x;
-    if (blockIdx.x * FIN_THREADS < n) // this CTA owns at least one key
+    // a CTA owns FIN_KEYS consecutive keys; 8 neighbouring lanes share one key and each ranks it against every 8th key of
+    // the list (lanes of one slice read the same shared-memory word: broadcast; the 8 slices read 8 consecutive words)
+    const uint32_t idx = blockIdx.x * FIN_KEYS + threadIdx.x / FIN_SLICES, slice = threadIdx.x % FIN_SLICES;
+    if (blockIdx.x * FIN_KEYS < n) // this CTA owns at least one key
     {
         const uint64_t mine = idx < n ? keys[idx] : ~0ull;
         uint32_t rank = 0;
@@ -621,12 +624,15 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(unsigned long long *coun
             for (uint32_t j = threadIdx.x; j < FIN_PIECE; j += FIN_THREADS) s_keys[j] = j < m ? keys[base + j] : ~0ull;
             __syncthreads();
             // keys are distinct (an occurrence key is unique), so "<" alone is a total order; padding (~0) never counts
-            const uint32_t mr = (m + 7u) & ~7u;
+            const uint32_t mr = (m + 63u) & ~63u;
 #pragma unroll 8
-            for (uint32_t j = 0; j < mr; j++) rank += s_keys[j] < mine ? 1u : 0u;
+            for (uint32_t j = slice; j < mr; j += FIN_SLICES) rank += s_keys[j] < mine ? 1u : 0u;
             __syncthreads();
         }
-        if (idx < n) d_pack[1 + rank] = mine;
+        rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+        rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+        rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+        if (idx < n && slice == 0) d_pack[1 + rank] = mine;
     }
     // the last CTA out resets the counters (counter[1] counts finished CTAs)
     __syncthreads();
@@ -647,7 +653,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(unsigned long long *coun
 // gets there when they exit — measured in run r2d: the overlapped version serialised anyway and slowed the scan's tail).
 int finish_scan(DevCtx &E, int slot, int want_sort, cudaStream_t stream)
 {
-    k_finish<<<PACK_KEYS / FIN_THREADS, FIN_THREADS, 0, stream>>>(slot_counter(E, slot), E.d_list[slot], E.key_cap, E.d_pack[slot],
+    k_finish<<<PACK_KEYS / FIN_KEYS, FIN_THREADS, 0, stream>>>(slot_counter(E, slot), E.d_list[slot], E.key_cap, E.d_pack[slot],
                                                                  (want_sort && E.d_list[slot]) ? 1 : 0);
     CK(cudaGetLastError());
     // count + (possibly) sorted keys to the host in one DMA of the whole packed row: 128 KiB over PCIe is ~5 us, cheaper than
