@@ -556,11 +556,12 @@ class Runner:
         def exchange(i):
             """N>1: row of step i -> rank 0 (enqueued behind whatever is already on the stream)."""
             xa[i].record(self.stream)
-            rc = L.krep_b200_export_packed_async(tickets[i & 1].value, g.row_ptr(), g.cap)
+            rc = L.krep_b200_export_packed_async(tickets[i & 1].value, g.row_ptr(), min(g.cap, 16384))
             assert rc == 0, L.krep_b200_last_error_string()
             g.post(i & 1)
             xb[i].record(self.stream)
 
+        self._tickets = tickets
         e0.record(self.stream)
         if overlapped:
             # software pipeline, two scans in flight: the stream always holds the next scan behind the current one; the
@@ -629,6 +630,14 @@ class Runner:
         self._last = dict(plan=plan, params=params, res=res, pats=pats, algo=algo, total=int(state["total"]),
                           own=own, avail=avail, g0=g0, spec=spec, halo=halo)
         return out
+
+    def drain(self):
+        """After an exception inside a workload: end whatever scans are still in flight so the next workload starts clean."""
+        from krep_b200.abi import DeviceResult
+        junk = DeviceResult()
+        for t in getattr(self, "_tickets", []):
+            self.L.krep_b200_scan_shard_end(t.value, C.byref(junk))
+        self.torch.cuda.synchronize()
 
     def release_last(self):
         last = getattr(self, "_last", None)
@@ -781,6 +790,7 @@ def _main(out_stream):
             try:
                 r = R.run(name, total, args.side_steps if (name, total_gib) in SIDE_WORKLOADS else 3, 3)
             except Exception as e:  # noqa: BLE001  (all ranks fail alike: sizes and code are identical)
+                R.drain()
                 r = {"error": str(e)} if rank == 0 else None
             R.release_last()
             if rank == 0 and r is not None:

@@ -215,7 +215,8 @@ DevCtx *ctx_get(int device)
         cudaSetDevice(device);
         return &E;
     }
-    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    static std::mutex mu[MAX_DEV]; // per device: contexts of different GPUs may be created concurrently
+    std::lock_guard<std::mutex> lk(mu[device]);
     if (!E.ready && ctx_create(E, device) != 0) return nullptr;
     return &E;
 }
