@@ -815,7 +815,7 @@ def _main(out_stream):
                                                "launching stream, inside the timed region; max over ranks)"),
         "kernel_ms_per_rank": head["kernel_ms_per_rank"], "ms_per_step_per_rank": head["ms_per_step_per_rank"],
         "exchange_ms": head["exchange_ms"], "exchange_ms_per_rank": head["exchange_ms_per_rank"],
-        "rank0_host_ms_per_step": head["rank0_host_ms_per_step"],
+        "rank0_host_ms_per_step": head["rank0_host_ms_per_step"], "steps_overlapped": head.get("steps_overlapped"),
         "gpu_launches": head["gpu_launches"], "clocks": clocks,
     }
     if e2e:
