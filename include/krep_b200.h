@@ -99,8 +99,12 @@ void krep_b200_warmup(void);
 /* The devices a search_func_t call spreads the caller's text over — the analogue of krep's thread count
  * (krep.c:2851-2905 cuts the file into one chunk per pool thread; here into one contiguous range per GPU, each range
  * streamed over that GPU's own PCIe link and scanned there, per-device occurrence lists merged by key on the host).
- * devices == NULL or n == 0 restores the default: KREP_B200_DEVICES=<count> from the environment, else one device per
- * 16 GiB of text (KREP_B200_DEVICE_SHARE_MB), primary device first. */
+ * devices == NULL or n == 0 restores the default: KREP_B200_DEVICES=<count> from the environment, else ONE device (from a
+ * pageable file mapping more devices add nothing: the host's page faults and staging copies are the limit; they pay for
+ * pinned text).  Start-up note: a process in which this library is the first user of CUDA hides the GPUs it will not use
+ * from the driver before CUDA initialises (cuInit enumerates every visible GPU: 6.8 s on an 8-GPU box against 0.4 s for
+ * one) — so choose the devices (this call, krep_b200_init, or KREP_B200_DEVICES / KREP_B200_KEEP_VISIBLE in the
+ * environment) before the first search. */
 void krep_b200_set_devices(const int *devices, int n);
 void krep_b200_shutdown(void);
 int krep_b200_last_error(void);           /* 0 = last call succeeded          */

@@ -53,6 +53,7 @@ static std::recursive_mutex g_mu;
 static std::mutex g_ctx_mu;
 static int g_primary = -1;
 static int g_visible = -1;
+static bool g_keep_visible = false; // the host chose its devices itself: leave CUDA_VISIBLE_DEVICES alone
 static uint64_t g_launches = 0;
 static thread_local float t_kernel_ms = 0.f;
 static const std::chrono::steady_clock::time_point g_t0 = std::chrono::steady_clock::now();
@@ -124,17 +125,39 @@ int visible_devices()
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
     if (g_visible >= 0) return g_visible;
-    // KREP_B200_LIMIT_VISIBLE=1: a one-shot process that will use k devices (KREP_B200_DEVICES, default 1) hides the
-    // others from the driver before CUDA initialises, if the user has not chosen a device set already — on an 8-GPU
-    // box cuInit enumerates every visible GPU (measured: profiles/r2_cli_timing.md)
-    if (getenv("KREP_B200_LIMIT_VISIBLE") && !getenv("CUDA_VISIBLE_DEVICES"))
+    // A process in which this library is the FIRST user of CUDA (the krep CLI) hides the GPUs it is not going to use from
+    // the driver before CUDA initialises: cuInit enumerates every visible GPU, which on the 8-GPU bench box costs 6.8 s
+    // against 0.4 s with one device visible (profiles/r2m8_cuinit.txt).  It will use KREP_B200_DEVICES devices (default
+    // 1) — the first ones of CUDA_VISIBLE_DEVICES if that is set.  Not done when the host manages devices itself
+    // (krep_b200_init / krep_b200_set_devices called first, or KREP_B200_KEEP_VISIBLE set); harmless when something else
+    // (torch) has initialised CUDA already — the variable is only read at initialisation.
+    if (!g_keep_visible && !getenv("KREP_B200_KEEP_VISIBLE"))
     {
         const char *v = getenv("KREP_B200_DEVICES");
         const int k = v && atoi(v) > 0 ? atoi(v) : 1;
         std::string list;
-        for (int d = 0; d < k && d < MAX_DEV; d++) list += (d ? "," : "") + std::to_string(d);
-        setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
-        trace("CUDA_VISIBLE_DEVICES=%s", list.c_str());
+        if (const char *cur = getenv("CUDA_VISIBLE_DEVICES"))
+        {
+            int taken = 0;
+            for (const char *q = cur; *q && taken < k;)
+            {
+                const char *e = strchr(q, ',');
+                const size_t len = e ? (size_t)(e - q) : strlen(q);
+                if (len)
+                {
+                    list += (taken ? "," : "") + std::string(q, len);
+                    taken++;
+                }
+                q += len + (e ? 1 : 0);
+            }
+        }
+        else
+            for (int d = 0; d < k && d < MAX_DEV; d++) list += (d ? "," : "") + std::to_string(d);
+        if (!list.empty())
+        {
+            setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
+            trace("CUDA_VISIBLE_DEVICES=%s", list.c_str());
+        }
     }
     int n = 0;
     trace("cudaGetDeviceCount ...");
@@ -998,6 +1021,7 @@ extern "C" {
 
 int krep_b200_init(int device)
 {
+    g_keep_visible = true;
     warm_join();
     std::lock_guard<std::recursive_mutex> lk(engine_mutex());
     clear_error();
@@ -1025,6 +1049,7 @@ int krep_b200_device_count(void)
     return visible_devices();
 }
 void krep_b200_warmup(void) { warm_start(); }
+void keep_devices_visible() { g_keep_visible = true; }
 
 float krep_b200_last_kernel_ms(void) { return t_kernel_ms; }
 uint64_t krep_b200_launch_count(void) { return g_launches; }

@@ -95,6 +95,7 @@ DevCtx *ctx_get(int device);     // creates the context on first use; nullptr af
 DevCtx *ctx_primary();           // ctx_get(primary_device())
 void engine_shutdown();
 void prewarm_host_path(DevCtx &C); // host_api.cu: rings + occurrence list for the pageable-text path
+void keep_devices_visible(); // the host manages devices itself: do not narrow CUDA_VISIBLE_DEVICES
 void warm_join();    // waits for the krep_b200_warmup thread, if one is running
 bool warm_running();
 

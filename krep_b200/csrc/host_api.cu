@@ -404,16 +404,13 @@ static std::vector<int> host_devices(size_t n)
     }
     const int prim = primary_device();
     if (prim < 0) return out;
+    // default: ONE device.  Measured (profiles/r2m2_cli_timing.txt, r2m8_cli_timing.txt): from a pageable file mapping a
+    // second GPU adds nothing — the host side (page faults + staging copies of one process) is the limit, 30-45 GB/s — and
+    // every further context costs 0.15-1.3 s of start-up.  KREP_B200_DEVICES=<k> (or krep_b200_set_devices) spreads the
+    // call over k devices, which pays for pinned host text (110 GB/s on 2, 185 GB/s on 8 devices from one NUMA node).
     int want = 1;
     const char *v = getenv("KREP_B200_DEVICES");
     if (v && *v && atoi(v) > 0) want = atoi(v);
-    else
-    {
-        // automatic: one more device per KREP_B200_DEVICE_SHARE_MB of text (default 16 GiB) — a context on another GPU
-        // costs more than its PCIe link saves on anything smaller
-        const size_t share = env_mb("KREP_B200_DEVICE_SHARE_MB", 16384);
-        want = (int)std::min<size_t>((n + share - 1) / share, (size_t)vis);
-    }
     want = std::max(1, std::min(want, vis));
     out.push_back(prim);
     for (int d = 0; d < vis && (int)out.size() < want; d++)
@@ -1000,6 +997,7 @@ bool krep_b200_ac_trie_root_has_outputs(const ac_trie_t *trie)
 void krep_b200_set_devices(const int *devices, int n)
 {
     std::lock_guard<std::recursive_mutex> lk(engine_mutex());
+    if (devices && n > 0) keep_devices_visible();
     g_devices.clear();
     for (int i = 0; devices && i < n; i++) g_devices.push_back(devices[i]);
 }
