@@ -119,6 +119,8 @@ __attribute__((destructor)) static void warm_at_exit()
     trace("library destructor (process exit)");
 }
 
+void keep_devices_visible() { g_keep_visible = true; }
+
 int visible_devices()
 {
     if (g_visible >= 0) return g_visible;
@@ -1049,7 +1051,6 @@ int krep_b200_device_count(void)
     return visible_devices();
 }
 void krep_b200_warmup(void) { warm_start(); }
-void keep_devices_visible() { g_keep_visible = true; }
 
 float krep_b200_last_kernel_ms(void) { return t_kernel_ms; }
 uint64_t krep_b200_launch_count(void) { return g_launches; }
