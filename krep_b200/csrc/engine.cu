@@ -616,15 +616,15 @@ int reset_counter(DevCtx &E, int slot, cudaStream_t stream)
 // memory — one fixed-size copy of the packed row behind the kernel — so that count AND sorted occurrences reach the host
 // with the one synchronisation the scan needs anyway: no CUB launches, no second read-back.
 //
-// The sort is a RANK sort spread over the GPU: a CTA owns 64 keys, streams the whole list through shared memory in
-// 2048-key pieces and counts, for each of its keys, the keys that order before it (8 lanes per key, each taking every
-// 8th list entry; lanes of one slice read the same word — a broadcast); that count is the key's final position.  n^2
-// compares, 10^8 for 10 240 keys, on 160 CTAs x 16 warps — instead of the 105 barrier-separated passes of a one-CTA
-// bitonic network (165 us measured, profiles/r2c_literal8_launches.csv; one thread per key without the 8-way split:
-// 86 us, r2e): with ~10^4 keys the quadratic algorithm is the one that uses the machine.
+// The sort is a RANK sort spread over the GPU: a CTA owns 32 keys, streams the whole list through shared memory in
+// 2048-key pieces and counts, for each of its keys, the keys that order before it (16 lanes per key, each taking every
+// 16th list entry; lanes of one slice read the same word — a broadcast); that count is the key's final position.  n^2
+// compares, 10^8 for 10 240 keys, on 320 CTAs x 16 warps — instead of the 105 barrier-separated passes of a one-CTA
+// bitonic network (165 us measured, profiles/r2c_literal8_launches.csv; one thread per key: 86 us, r2e; 8 lanes per key:
+// 51 us, r2f): with ~10^4 keys the quadratic algorithm is the one that uses the machine.
 // The last CTA to finish zeroes the scan counter and the done-counter for the slot's next scan.
 // ---------------------------------------------------------------------------------------------
-static constexpr int FIN_THREADS = 512, FIN_SLICES = 8, FIN_KEYS = FIN_THREADS / FIN_SLICES, FIN_PIECE = 2048;
+static constexpr int FIN_THREADS = 512, FIN_SLICES = 16, FIN_KEYS = FIN_THREADS / FIN_SLICES, FIN_PIECE = 2048;
 
 __global__ void __launch_bounds__(FIN_THREADS) k_finish(unsigned long long *counter, const uint64_t *__restrict__ keys, uint64_t cap,
                                                         uint64_t *d_pack, int want_sort)
@@ -637,8 +637,9 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(unsigned long long *coun
     if (blockIdx.x == 0 && threadIdx.x == 0) d_pack[0] = cnt;
     const bool sorting = want_sort && cnt != 0 && cnt <= PACK_KEYS && cnt <= cap;
     const uint32_t n = sorting ? (uint32_t)cnt : 0u;
-    // a CTA owns FIN_KEYS consecutive keys; 8 neighbouring lanes share one key and each ranks it against every 8th key of
-    // the list (lanes of one slice read the same shared-memory word: broadcast; the 8 slices read 8 consecutive words)
+    // a CTA owns FIN_KEYS consecutive keys; FIN_SLICES neighbouring lanes share one key and each ranks it against every
+    // FIN_SLICES-th key of the list (lanes of one slice read the same shared-memory word: broadcast; the slices read
+    // consecutive words)
     const uint32_t idx = blockIdx.x * FIN_KEYS + threadIdx.x / FIN_SLICES, slice = threadIdx.x % FIN_SLICES;
     if (blockIdx.x * FIN_KEYS < n) // this CTA owns at least one key
     {
@@ -655,9 +656,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish(unsigned long long *coun
             for (uint32_t j = slice; j < mr; j += FIN_SLICES) rank += s_keys[j] < mine ? 1u : 0u;
             __syncthreads();
         }
-        rank += __shfl_xor_sync(0xffffffffu, rank, 1);
-        rank += __shfl_xor_sync(0xffffffffu, rank, 2);
-        rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+#pragma unroll
+        for (int o = 1; o < FIN_SLICES; o <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
         if (idx < n && slice == 0) d_pack[1 + rank] = mine;
     }
     // the last CTA out resets the counters (counter[1] counts finished CTAs)
