@@ -593,3 +593,44 @@ def test_bench_workloads_equal_the_reference_on_the_synthetic_corpus(name, gib, 
     finally:
         p.struct.ac_trie = None
         L.krep_b200_plan_destroy(plan)
+
+
+def test_two_scans_in_flight_and_async_export():
+    """Two scans in flight on one device (krep_b200_scan_shard_begin twice, then _end in order): each has its own list and
+    counter, each _end waits for its own finish kernel only; krep_b200_export_packed_async enqueues the row [count, keys]
+    before the host knows the count.  Results must equal the one-at-a-time results."""
+    from krep_b200.abi import DeviceResult, Shard
+    L = lib.load()
+    n = 48 * (1 << 20)
+    spec = lib.make_spec(15, 16, 1 << 14, NEEDLE, 0)          # ~3000 occurrences
+    dev = gu.device_corpus(spec, 0, n)
+    p = Params(NEEDLE)
+    plan = L.krep_b200_plan_create(p.ref(), ALGO_SSE42)
+    lib.check(L)
+    try:
+        half = n // 2
+        shards = [Shard(dev.data_ptr(), half + 16, 0, half, 0, -1, -1), Shard(dev.data_ptr(), n, half, n, 0, -1, -1)]
+        want = [gu.collect(plan, p, gu.scan(plan, dev, s.avail_len, own_begin=s.own_begin, own_end=s.own_end)) for s in shards]
+        rows = [torch.zeros(16385, dtype=torch.int64, device="cuda") for _ in range(2)]
+        for rep in range(3):
+            tickets = [C.c_int(-1), C.c_int(-1)]
+            for i in range(2):
+                assert L.krep_b200_scan_shard_begin(plan, C.byref(shards[i]), 1, None, C.byref(tickets[i])) == 0
+                assert L.krep_b200_export_packed_async(tickets[i].value, rows[i].data_ptr(), 16384) == 0
+            third = C.c_int(-1)
+            assert L.krep_b200_scan_shard_begin(plan, C.byref(shards[0]), 1, None, C.byref(third)) != 0   # only two in flight
+            assert L.krep_b200_last_error() != 0
+            for i in range(2):
+                out = DeviceResult()
+                assert L.krep_b200_scan_shard_end(tickets[i].value, C.byref(out)) == 0
+                lib.check(L)
+                got = gu.collect(plan, p, out)
+                assert got == want[i], (rep, i, got[0], want[i][0])
+            torch.cuda.synchronize()
+            for i in range(2):
+                host = rows[i].cpu()
+                cnt = int(host[0])
+                assert cnt == want[i][0]
+                assert [int(k) >> 3 for k in host[1:1 + cnt].tolist()] == [s for s, _ in want[i][1]]
+    finally:
+        L.krep_b200_plan_destroy(plan)
