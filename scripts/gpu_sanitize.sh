@@ -16,7 +16,9 @@ text = bytes(t[:300_000])
 chk = ou.reference() or ou.port()
 cases = [("sse42", [b"needle"], {}), ("boyer_moore", [b"NeEdLe"], dict(case_sensitive=False)), ("boyer_moore", [b"ab"], dict(whole_word=True)),
          ("memchr", [b"x"], {}), ("memchr_short", [b"ab"], dict(case_sensitive=False)), ("kmp", [b"abab"], {}),
-         ("avx2", [b"needle the quick ab"], {}), ("boyer_moore", [b"the"], dict(count=True)),
+         ("avx2", [b"needle the quick ab"], {}), ("boyer_moore", [b"the"], dict(count=True)),              # fused -c, window filter
+         ("boyer_moore", [b"needle_7"], dict(count=True, whole_word=True)), ("memchr", [b"x"], dict(count=True)),  # fused -c, aligned filter / 1 byte
+         ("sse42", [b"ab"], dict(only_matching=True)),                                                       # masked window kernel: warp-cooperative emission
          ("aho_corasick", [b"needle", b"haystack", b"quick the", b"fox_1 "], {}),                    # shortest 6: tri
          ("aho_corasick", [b"needle_7", b"haystack", b"quick the"], dict(case_sensitive=False)),      # shortest 8: quad, fold
          ("aho_corasick", [b"ab", b"needle", b"x"], {}), ("aho_corasick", [b"abab", b"quick"], {}),   # short patterns: k_ac_scan s=1, s=2
@@ -27,6 +29,6 @@ for func, pats, opts in cases:
     assert got == want, (func, pats, opts, got[0], want[0])
     print("ok", func, pats[0], got[0], flush=True)
 PY
-for tool in memcheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 3 python /tmp/san_case.py > $O/sanitize_$tool.log 2>&1; echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|^ok|Error|hazard" $O/sanitize_$tool.log | tail -20
+for tool in ${SAN_TOOLS:-memcheck racecheck}; do
+  timeout ${SAN_TIMEOUT:-900} compute-sanitizer --tool $tool --error-exitcode 3 python /tmp/san_case.py > $O/sanitize_$tool.log 2>&1; echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|^ok|Error|hazard" $O/sanitize_$tool.log | tail -20
 done

@@ -22,6 +22,16 @@ def test_patch_anchors_apply_to_the_reference_source():
     assert "select_search_algorithm_cpu" in src and "krep_b200_select_search_algorithm(params)" in src
 
 
+def _visible_gpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout
+        n = sum(1 for ln in out.splitlines() if ln.startswith("GPU "))
+    except OSError:
+        return 0
+    cvd = os.environ.get("CUDA_VISIBLE_DEVICES")
+    return min(n, len([x for x in cvd.split(",") if x])) if cvd else n
+
+
 def _text(rng, n):
     words = [b"the", b"quick", b"Brown", b"fox_1", b"needle", b"NEEDLE", b"Needle", b"ab", b"abab", b"aaa", b"x",
              b"haystack", b"needleneedle", b"aba"]
@@ -67,6 +77,16 @@ def test_gpu_krep_prints_what_stock_krep_prints(tmp_path, size):
         a = subprocess.run([stock, "-t", "1", "--color=never", *flags, str(path)], capture_output=True)
         b = subprocess.run([gpu, "--color=never", *flags, str(path)], capture_output=True)
         assert (b.returncode, b.stdout) == (a.returncode, a.stdout), (flags, a.stdout[:300], b.stdout[:300], b.stderr[:300])
+    # the same file spread over every GPU of the box inside the one search call (1 MiB chunks so that every device gets a
+    # range): the output must not change
+    ndev = _visible_gpus()
+    if size == 9_000_000 and ndev >= 2:
+        env = dict(os.environ, KREP_B200_DEVICES=str(ndev), KREP_B200_STAGE_MB="1", KREP_B200_CHUNK_MB="1")
+        env.pop("KREP_B200_KEEP_VISIBLE", None)
+        for flags in cases + [["-o", "-e", "needle", "-e", "fox_1 ne", "-e", "ab"]]:
+            a = subprocess.run([stock, "-t", "1", "--color=never", *flags, str(path)], capture_output=True)
+            b = subprocess.run([gpu, "--color=never", *flags, str(path)], capture_output=True, env=env)
+            assert (b.returncode, b.stdout) == (a.returncode, a.stdout), (ndev, flags, a.stdout[:300], b.stdout[:300], b.stderr[:300])
     if size != 900:
         return
     # -s STRING and stdin go through search_string (krep.c:1999): no sort, bare count
