@@ -62,3 +62,30 @@ def test_fold_of_shard_records_equals_single_chunk_count():
             got = L.krep_b200_combine_line_counts(recs, nsh, SIZE_MAX)
             assert got == want, (text, cuts, [(r.lines, r.flags) for r in recs], got, want)
             assert L.krep_b200_combine_line_counts(recs, nsh, 2) == min(want, 2)
+
+
+def test_merge_keys_is_a_stable_k_way_merge():
+    """krep_b200_merge_keys on random ascending lists (empty lists, duplicates across lists, aliasing dst with the first
+    list) == sorted concatenation."""
+    import ctypes as C
+    L = lib.load()
+    rng = random.Random(9)
+    for trial in range(300):
+        k = rng.randint(1, 9)
+        lists = [sorted(rng.randrange(0, 1 << rng.choice([8, 40, 62])) for _ in range(rng.choice([0, 0, 1, 5, 40, 300]))) for _ in range(k)]
+        total = sum(map(len, lists))
+        bufs = [(C.c_uint64 * max(len(x), 1))(*x) for x in lists]
+        ptrs = (C.c_void_p * k)(*[C.addressof(b) for b in bufs])
+        cnts = (C.c_uint64 * k)(*[len(x) for x in lists])
+        dst = (C.c_uint64 * max(total, 1))()
+        n = L.krep_b200_merge_keys(ptrs, cnts, k, C.cast(dst, C.c_void_p))
+        assert n == total and list(dst[:total]) == sorted(sum(lists, []))
+    # rows of one matrix, dst aliasing nothing: what sharding.merge_rows does
+    import torch
+    from krep_b200 import sharding
+    rows = torch.zeros((3, 6), dtype=torch.int64)
+    data = [[5, 9, 30], [1, 2], [7, 8, 100, 200]]
+    for r, xs in enumerate(data):
+        rows[r, 0] = len(xs)
+        rows[r, 1:1 + len(xs)] = torch.tensor(xs)
+    assert sharding.merge_rows(rows, [len(x) for x in data]).tolist() == sorted(sum(data, []))
