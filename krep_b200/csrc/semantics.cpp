@@ -6,8 +6,11 @@
 // looked up in the caller's host buffer around occurrences only (memrchr/memchr, as the reference
 // does in find_line_start/find_line_end, krep.c:363-408).
 #define _GNU_SOURCE
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <omp.h>
+#include <vector>
 #include "common.h"
 
 namespace kb {
@@ -450,14 +453,32 @@ static bool replay_keep_all(int algo, const search_params_t *P, uint32_t m, cons
     if (P->count_lines_mode || P->max_count != SIZE_MAX) return false;
     if (algo != KREP_B200_ALGO_BMH && algo != KREP_B200_ALGO_KMP && algo != KREP_B200_ALGO_SSE42 && algo != KREP_B200_ALGO_MEMCHR)
         return false;
-    uint64_t prev = 0, kept = 0;
-    for (size_t j = 0; j < r.n; j++)
+    // long lists (the density sweep: 10^7..10^8 occurrences) are validated and copied by several host threads, each on
+    // a contiguous slice of the list; short ones stay on the calling thread
+    const int nt = r.n >= (1u << 20) ? std::min(8, std::max(1, omp_get_max_threads())) : 1;
+    std::vector<uint64_t> kept_of((size_t)nt + 1, 0);
+    bool bad = false;
+#pragma omp parallel for num_threads(nt) schedule(static, 1) reduction(|| : bad)
+    for (int t = 0; t < nt; t++)
     {
-        const uint64_t k = r.keys[j], s = k >> LIT_TAG_BITS;
-        if (!(k & 4) || (j && s < prev + m)) return false; // a prefix-only key, or an overlap: full replay
-        prev = s;
-        kept += !P->whole_word || (k & 3) == 3;
+        const size_t a = r.n * (size_t)t / (size_t)nt, b = r.n * (size_t)(t + 1) / (size_t)nt;
+        uint64_t prev = a ? (r.keys[a - 1] >> LIT_TAG_BITS) : 0, kept = 0;
+        for (size_t j = a; j < b; j++)
+        {
+            const uint64_t k = r.keys[j], s = k >> LIT_TAG_BITS;
+            if (!(k & 4) || (j && s < prev + m)) // a prefix-only key, or an overlap: full replay
+            {
+                bad = true;
+                break;
+            }
+            prev = s;
+            kept += !P->whole_word || (k & 3) == 3;
+        }
+        kept_of[(size_t)t + 1] = kept;
     }
+    if (bad) return false;
+    for (int t = 0; t < nt; t++) kept_of[(size_t)t + 1] += kept_of[(size_t)t];
+    const uint64_t kept = kept_of[(size_t)nt];
     *out = kept;
     if (!(P->track_positions && res) || kept == 0) return true;
     uint64_t cap = res->capacity ? res->capacity : 16;
@@ -469,15 +490,21 @@ static bool replay_keep_all(int algo, const search_params_t *P, uint32_t m, cons
         res->positions = np;
         res->capacity = cap;
     }
-    match_position_t *o = res->positions + res->count;
-    for (size_t j = 0; j < r.n; j++)
+    match_position_t *const o0 = res->positions + res->count;
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+    for (int t = 0; t < nt; t++)
     {
-        const uint64_t k = r.keys[j];
-        if (P->whole_word && (k & 3) != 3) continue;
-        const size_t s = (size_t)((k >> LIT_TAG_BITS) - r.base);
-        o->start_offset = s;
-        o->end_offset = s + m;
-        o++;
+        const size_t a = r.n * (size_t)t / (size_t)nt, b = r.n * (size_t)(t + 1) / (size_t)nt;
+        match_position_t *o = o0 + kept_of[(size_t)t];
+        for (size_t j = a; j < b; j++)
+        {
+            const uint64_t k = r.keys[j];
+            if (P->whole_word && (k & 3) != 3) continue;
+            const size_t s = (size_t)((k >> LIT_TAG_BITS) - r.base);
+            o->start_offset = s;
+            o->end_offset = s + m;
+            o++;
+        }
     }
     res->count += kept;
     return true;

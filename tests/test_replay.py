@@ -172,3 +172,35 @@ def test_count_lines_replay_from_line_bounds_only(func):
         assert int(cnt) == want[0], (func, pats, text, opts, int(cnt), want[0])
         n_checked += 1
     assert n_checked > 300
+
+
+def test_bulk_replay_of_a_long_list_is_the_same_on_several_threads():
+    """Lists of 2^20 keys and more take the multi-threaded bulk path of the replay (csrc/semantics.cpp replay_keep_all):
+    slices validated and copied by several host threads.  Must equal the straightforward answer, with and without -w
+    rejects, and fall back to the cursor replay when an overlap sits exactly on a slice boundary."""
+    import numpy as np
+    L = lib.load()
+    n, m = (1 << 20) + 12345, 3
+    rng = np.random.default_rng(5)
+    starts = np.arange(n, dtype=np.uint64) * 5 + 2
+    for whole_word in (False, True):
+        tags = rng.choice(np.array([7, 7, 7, 6, 5, 4], dtype=np.uint64), size=n) if whole_word else np.full(n, 7, dtype=np.uint64)
+        keys = np.ascontiguousarray((starts << np.uint64(3)) | tags)
+        p = Params(b"abc", whole_word=whole_word)
+        res = L.krep_b200_match_result_init(16)
+        cnt = L.krep_b200_replay(ALGO_BMH, p.ref(), False, keys.ctypes.data_as(C.POINTER(C.c_uint64)), n, None, int(starts[-1]) + 10, res)
+        keep = (tags & np.uint64(3)) == 3
+        assert cnt == int(keep.sum()) == res.contents.count
+        got = np.ctypeslib.as_array(C.cast(res.contents.positions, C.POINTER(C.c_uint64)), shape=(int(cnt), 2))
+        assert np.array_equal(got[:, 0], starts[keep]) and np.array_equal(got[:, 1], starts[keep] + np.uint64(m))
+        L.krep_b200_match_result_free(res)
+    # an overlapping pair right at a slice boundary (n * t / 8): the bulk path must refuse, the cursor walk decides
+    keys2 = (starts << np.uint64(3)) | np.uint64(7)
+    b = n * 3 // 8
+    keys2[b] = ((starts[b - 1] + np.uint64(1)) << np.uint64(3)) | np.uint64(7)
+    keys2 = np.ascontiguousarray(keys2)
+    for algo, expect in ((ALGO_BMH, n), (ALGO_KMP, n - 1)):        # BMH keeps overlapping occurrences, KMP does not
+        res = L.krep_b200_match_result_init(16)
+        cnt = L.krep_b200_replay(algo, Params(b"aaa").ref(), False, keys2.ctypes.data_as(C.POINTER(C.c_uint64)), n, None, int(starts[-1]) + 10, res)
+        assert cnt == expect == res.contents.count
+        L.krep_b200_match_result_free(res)
