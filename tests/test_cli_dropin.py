@@ -59,6 +59,9 @@ def test_gpu_krep_prints_what_stock_krep_prints(tmp_path, size):
     gpu = build_krep_gpu.build()
     if not stock or not gpu:
         pytest.skip("stock or GPU-backed krep binary not available (built in the container that has /root/reference)")
+    # the CLI is a one-shot process: let the library hide the GPUs it does not use (conftest keeps them visible for the
+    # in-process tests), or every invocation pays cuInit for the whole box
+    env_gpu = {k: v for k, v in os.environ.items() if k != "KREP_B200_KEEP_VISIBLE"}
     rng = random.Random(size)
     path = tmp_path / "corpus.txt"
     path.write_bytes(_text(rng, size))
@@ -75,14 +78,13 @@ def test_gpu_krep_prints_what_stock_krep_prints(tmp_path, size):
                  ["-c", "-m", "1000", "the quick Brown fox_1 needle"]]
     for flags in cases:
         a = subprocess.run([stock, "-t", "1", "--color=never", *flags, str(path)], capture_output=True)
-        b = subprocess.run([gpu, "--color=never", *flags, str(path)], capture_output=True)
+        b = subprocess.run([gpu, "--color=never", *flags, str(path)], capture_output=True, env=env_gpu)
         assert (b.returncode, b.stdout) == (a.returncode, a.stdout), (flags, a.stdout[:300], b.stdout[:300], b.stderr[:300])
     # the same file spread over every GPU of the box inside the one search call (1 MiB chunks so that every device gets a
     # range): the output must not change
     ndev = _visible_gpus()
     if size == 9_000_000 and ndev >= 2:
-        env = dict(os.environ, KREP_B200_DEVICES=str(ndev), KREP_B200_STAGE_MB="1", KREP_B200_CHUNK_MB="1")
-        env.pop("KREP_B200_KEEP_VISIBLE", None)
+        env = dict(env_gpu, KREP_B200_DEVICES=str(ndev), KREP_B200_STAGE_MB="1", KREP_B200_CHUNK_MB="1")
         for flags in cases + [["-o", "-e", "needle", "-e", "fox_1 ne", "-e", "ab"]]:
             a = subprocess.run([stock, "-t", "1", "--color=never", *flags, str(path)], capture_output=True)
             b = subprocess.run([gpu, "--color=never", *flags, str(path)], capture_output=True, env=env)
@@ -92,9 +94,9 @@ def test_gpu_krep_prints_what_stock_krep_prints(tmp_path, size):
     # -s STRING and stdin go through search_string (krep.c:1999): no sort, bare count
     for flags in (["-c", "-s", "aba", "abababa"], ["-i", "-o", "-s", "NEEDLE", "a needle in a Needle stack"]):
         a = subprocess.run([stock, "--color=never", *flags], capture_output=True)
-        b = subprocess.run([gpu, "--color=never", *flags], capture_output=True)
+        b = subprocess.run([gpu, "--color=never", *flags], capture_output=True, env=env_gpu)
         assert (b.returncode, b.stdout) == (a.returncode, a.stdout), (flags, a.stdout, b.stdout, b.stderr)
     for flags in (["-o", "-e", "he", "-e", "she", "-e", "hers"], ["-c", "she"]):
         a = subprocess.run([stock, "--color=never", *flags], input=b"ushers and hers\nshe sells\n", capture_output=True)
-        b = subprocess.run([gpu, "--color=never", *flags], input=b"ushers and hers\nshe sells\n", capture_output=True)
+        b = subprocess.run([gpu, "--color=never", *flags], input=b"ushers and hers\nshe sells\n", capture_output=True, env=env_gpu)
         assert (b.returncode, b.stdout) == (a.returncode, a.stdout), (flags, a.stdout, b.stdout, b.stderr)
